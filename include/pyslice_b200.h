@@ -1,0 +1,106 @@
+/* pyslice_b200 -- C ABI of the B200 (sm_100a) multislice + TACAW engine (libpsb.so).
+ *
+ * The reference (h-walk/PySlice) has no FFI: its hot path is a chain of torch calls inside Python
+ * classes.  These entry points are what a binding for that path replaces; each one cites the
+ * reference lines whose arithmetic it performs (paths relative to the reference checkout).  See
+ * INTEGRATION.md for the ctypes stubs a PySlice maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative psb_status; psb_last_error() gives the
+ *     text for the calling thread;
+ *   - all array arguments are caller-owned DEVICE pointers on the current CUDA device
+ *     (torch: tensor.data_ptr()); `stream` is a cudaStream_t passed as void* (NULL = default);
+ *   - complex64 arrays are interleaved (re, im) float pairs; images are row-major (nx, ny), ny fastest;
+ *   - calls are asynchronous on `stream` unless stated; no callbacks, no exceptions, no host
+ *     fallback -- without a CUDA device every call fails with PSB_ERR_CUDA.
+ */
+#ifndef PYSLICE_B200_H
+#define PYSLICE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    PSB_OK = 0,
+    PSB_ERR_INVALID = -1,
+    PSB_ERR_UNSUPPORTED = -2,
+    PSB_ERR_CUDA = -3,
+    PSB_ERR_NOMEM = -4
+} psb_status;
+
+typedef struct { float re, im; } psb_c64;
+
+int psb_version(void);
+const char* psb_last_error(void);
+/* number of SMs of the current device (148 on B200); used by the host to size frame batches */
+int psb_sm_count(void);
+/* drop cached FFT tables of all devices */
+void psb_release_tables(void);
+
+/* ---- atom -> slice binning: src/multislice/potentials.py:297-317 (+ bounds :304-305) -------------
+ * positions (F, A, 3) float64; type_idx (A) dense type index in [0, ntypes);
+ * lo, hi (nz) float64 slice bounds evaluated by the host with the reference's expressions.
+ * Outputs: offsets (F, nz*ntypes+1) exclusive segment offsets (segment = slice*ntypes + type);
+ *          atom_list / ux / uy (F, 2*A): atom index and frac(x/Lx), frac(y/Ly) as 32-bit fixed point,
+ *          grouped by segment, ascending atom index inside a segment (deterministic).
+ * seg_scratch: (F, A, 2) int32 workspace.  lx_eff = nx*dx, ly_eff = ny*dy. */
+int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames, int n_atoms, int ntypes,
+                  int nz, const double* lo, const double* hi, double dz, double lx_eff, double ly_eff,
+                  int32_t* seg_scratch, int32_t* offsets, int32_t* atom_list, uint32_t* ux, uint32_t* uy,
+                  void* stream);
+
+/* ---- projected potential -> transmission: potentials.py:319-342 and multislice.py:281-282 --------
+ * formfactors (ntypes, nx, ny) float32 = Kirkland f_e on the fftfreq grid (host table, potentials.py:86-96).
+ * t_out (F, nz, nx, ny) complex64 = exp(i*sigma*V), V = Re IFFT2(S) * scale  with scale = 1/(dx^2 dy^2)
+ * (the 1/(nx*ny) of the inverse FFT is applied internally).  v_out (same shape, float32) optional. */
+int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
+                           int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
+                           float scale, float sigma, psb_c64* t_out, float* v_out, void* stream);
+
+/* t = exp(i*sigma*V) for a user-supplied real potential (Propagate() on a Potential object) */
+int psb_transmission_from_potential(const float* v, psb_c64* t, long long n, float sigma, void* stream);
+
+/* ---- generic batched 2-D FFT, unnormalised forward / inverse*scale: torch.fft.fft2/ifft2 call sites
+ * multislice.py:124,188,218  (probe construction, defocus).  In place allowed. */
+int psb_fft2(const psb_c64* src, psb_c64* dst, int batch, int nx, int ny, int inverse, float scale, void* stream);
+
+/* ---- shifted probes: multislice.py:216-231.  out[p] = ifft2(base_k * ramp_x[p][:,None] * ramp_y[p][None,:]) */
+int psb_shift_probes(const psb_c64* base_k, const psb_c64* ramp_x, const psb_c64* ramp_y, int n_probes,
+                     int nx, int ny, psb_c64* out, void* stream);
+
+/* ---- multislice propagation + exit FFT: multislice.py:278-294, calculators.py:285-290,185-186 -----
+ * probes (P, nx, ny); t (F, nz, nx, ny); prop_x (nx), prop_y (ny): separable Fresnel propagator
+ * exp(-i*pi*lambda*dz*k^2) with the 1/(nx*ny) of the FFT pair folded in by the host.
+ * psi_work (F*P, nx, ny) scratch, image index = frame*P + probe.
+ * mode 0: exit waves in real space are left in psi_work (Propagate()).
+ * mode 1: wf_out[layer*stride_layer + probe*stride_probe + frame*stride_frame + kx'*ny + ky'] receives
+ *         fftshift(fft2(psi)) after the transmission of every `layer_every`-th slice (0: exit only;
+ *         the exit wave is always the last layer). */
+int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_probes, int nz, int nx, int ny,
+                  const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out,
+                  long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
+                  void* stream);
+
+/* ---- TACAW: tacaw_data.py:89-104.  intensity[p, w, pix] = |fftshift_t FFT_t(psi - mean_t psi)|^2
+ * wf element (p, f, pix) at wf[p*stride_probe + f*stride_frame + pix]; intensity (P, T, npix) float32. */
+int psb_tacaw_intensity(const psb_c64* wf, long long stride_probe, long long stride_frame, int n_probes,
+                        int n_frames, long long npix, float* intensity, void* stream);
+
+/* ---- reducers: tacaw_data.py:124,137,198,211,277,293; haadf_data.py:60 -----------------------------
+ * out[row] = sum_pix in[row*row_stride + pix] * mask[pix] (mask may be NULL), float64 results */
+int psb_sum_pixels(const float* in, const float* mask, int rows, long long row_stride, long long npix,
+                   double* out, void* stream);
+/* same with |z| of a complex input (HAADF detector sum) */
+int psb_sum_abs_pixels(const psb_c64* in, const float* mask, int rows, long long row_stride, long long npix,
+                       double* out, void* stream);
+/* out[g, pix] = sum_t in[g, t, pix] */
+int psb_sum_frames(const float* in, int groups, int n_frames, long long npix, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYSLICE_B200_H */

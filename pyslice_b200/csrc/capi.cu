@@ -1,0 +1,279 @@
+// C ABI of libpsb.so: argument checking and kernel orchestration (see include/pyslice_b200.h).
+#include "../../include/pyslice_b200.h"
+
+#include "line_pass.cuh"
+#include "potential_kernels.cuh"
+#include "psb_rt.h"
+#include "reduce_kernels.cuh"
+#include "tables.h"
+
+using namespace psb;
+
+namespace {
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline float2* f2(psb_c64* p) { return reinterpret_cast<float2*>(p); }
+inline const float2* f2(const psb_c64* p) { return reinterpret_cast<const float2*>(p); }
+
+template <class K, class P>
+int go(dim3 grid, size_t smem, cudaStream_t s, const P& p, const char* what) {
+    cudaError_t e = launch<K>(grid, smem, s, p);
+    if (e != cudaSuccess) {
+#ifndef PSB_EMU
+        return fail(PSB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+#else
+        return PSB_ERR_CUDA;
+#endif
+    }
+    return PSB_OK;
+}
+
+PassParams base_params() {
+    PassParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.scale = 1.0f;
+    p.mul_img_div = 1;
+    p.probes = 1;
+    return p;
+}
+
+// rows-oriented pass over (n_img, nx, ny) images: lines are the nx rows of length ny
+void rows_geometry(PassParams& p, int nx, int ny) {
+    p.nlines = nx;
+    p.line_len = ny;
+    p.line_stride = ny;
+    p.elem_stride = 1;
+}
+// cols-oriented pass: lines are the ny columns of length nx
+void cols_geometry(PassParams& p, int nx, int ny) {
+    p.nlines = ny;
+    p.line_len = nx;
+    p.line_stride = 1;
+    p.elem_stride = ny;
+}
+}  // namespace
+
+extern "C" {
+
+int psb_version(void) { return 100; }
+const char* psb_last_error(void) { return last_error(); }
+int psb_sm_count(void) { return rt::sm_count(); }
+void psb_release_tables(void) { free_all_tables(); }
+
+int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames, int n_atoms, int ntypes,
+                  int nz, const double* lo, const double* hi, double dz, double lx_eff, double ly_eff,
+                  int32_t* seg_scratch, int32_t* offsets, int32_t* atom_list, uint32_t* ux, uint32_t* uy,
+                  void* stream) {
+    if (!positions || !type_idx || !lo || !hi || !seg_scratch || !offsets || !atom_list || !ux || !uy)
+        return fail(PSB_ERR_INVALID, "psb_bin_atoms: null pointer");
+    if (n_frames < 0 || n_atoms < 0 || ntypes < 1 || nz < 1 || !(dz > 0) || !(lx_eff > 0) || !(ly_eff > 0))
+        return fail(PSB_ERR_INVALID, "psb_bin_atoms: bad sizes");
+    if (n_frames > 65535 || (long long)nz * ntypes > 0x7fffffffLL)
+        return fail(PSB_ERR_UNSUPPORTED, "psb_bin_atoms: too many frames per call (max 65535)");
+    cudaStream_t s = as_stream(stream);
+    const int nseg = nz * ntypes;
+    int rc = rt::zero(offsets, (size_t)n_frames * (nseg + 1) * sizeof(int), s);
+    if (rc != PSB_OK || n_frames == 0) return rc;
+    BinParams p;
+    p.pos = positions; p.type_idx = type_idx; p.F = n_frames; p.A = n_atoms; p.nz = nz; p.ntypes = ntypes;
+    p.lo = lo; p.hi = hi; p.inv_dz = 1.0 / dz; p.inv_lx = 1.0 / lx_eff; p.inv_ly = 1.0 / ly_eff;
+    p.seg_of = seg_scratch; p.offsets = offsets; p.atom_list = atom_list; p.ux = ux; p.uy = uy;
+    p.cap = 2 * n_atoms;
+    if (n_atoms > 0) {
+        rc = go<BinAssign>(dim3((n_atoms + 255) / 256, n_frames), 0, s, p, "bin_assign");
+        if (rc != PSB_OK) return rc;
+    }
+    rc = go<BinScan>(dim3(n_frames), BinScan::kThreads * sizeof(int), s, p, "bin_scan");
+    if (rc != PSB_OK) return rc;
+    if (n_atoms > 0) rc = go<BinCompact>(dim3(nseg, n_frames), BinCompact::kThreads * sizeof(int), s, p, "bin_compact");
+    return rc;
+}
+
+int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
+                           int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
+                           float scale, float sigma, psb_c64* t_out, float* v_out, void* stream) {
+    if (!offsets || !ux || !uy || !formfactors || !t_out) return fail(PSB_ERR_INVALID, "psb_build_transmission: null pointer");
+    if (n_frames < 0 || nz < 1 || nx < 1 || ny < 1 || ntypes < 1) return fail(PSB_ERR_INVALID, "psb_build_transmission: bad sizes");
+    if (n_frames == 0) return PSB_OK;
+    if (nz > 65535 || n_frames > 65535 || (long long)n_frames * nz > 65535)
+        return fail(PSB_ERR_UNSUPPORTED, "psb_build_transmission: frames*slices per call must be <= 65535");
+    cudaStream_t s = as_stream(stream);
+    SfParams sp;
+    sp.offsets = offsets; sp.ux = ux; sp.uy = uy; sp.cap = 2 * n_atoms; sp.nz = nz; sp.ntypes = ntypes;
+    sp.nx = nx; sp.ny = ny; sp.ff = formfactors; sp.out = f2(t_out);
+    const int T = StructureFactor::TILE;
+    dim3 grid(((nx + T - 1) / T) * ((ny + T - 1) / T), nz, n_frames);
+    int rc = go<StructureFactor>(grid, StructureFactor::kSmem, s, sp, "structure_factor");
+    if (rc != PSB_OK) return rc;
+
+    const long long img = (long long)nx * ny;
+    PassParams p = base_params();
+    p.src = f2(t_out); p.dst = f2(t_out); p.src_img_stride = img; p.dst_img_stride = img;
+    cols_geometry(p, nx, ny);
+    rc = launch_line_pass(PASS_INV_COLS, p, n_frames * nz, s);
+    if (rc != PSB_OK) return rc;
+    rows_geometry(p, nx, ny);
+    p.scale = scale / ((float)nx * (float)ny);
+    p.sigma = sigma;
+    p.vout = v_out;
+    return launch_line_pass(PASS_RI, p, n_frames * nz, s);
+}
+
+int psb_transmission_from_potential(const float* v, psb_c64* t, long long n, float sigma, void* stream) {
+    if (!v || !t || n < 0) return fail(PSB_ERR_INVALID, "psb_transmission_from_potential: bad argument");
+    if (n == 0) return PSB_OK;
+    TransmitParams p{v, f2(t), n, sigma};
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    return go<Transmit>(dim3((unsigned)blocks), 0, as_stream(stream), p, "transmit");
+}
+
+int psb_fft2(const psb_c64* src, psb_c64* dst, int batch, int nx, int ny, int inverse, float scale, void* stream) {
+    if (!src || !dst || batch < 0 || nx < 1 || ny < 1) return fail(PSB_ERR_INVALID, "psb_fft2: bad argument");
+    cudaStream_t s = as_stream(stream);
+    const long long img = (long long)nx * ny;
+    for (int b0 = 0; b0 < batch; b0 += 65535) {
+        const int nb = batch - b0 < 65535 ? batch - b0 : 65535;
+        PassParams p = base_params();
+        p.src = f2(src) + b0 * img; p.dst = f2(dst) + b0 * img; p.src_img_stride = img; p.dst_img_stride = img;
+        rows_geometry(p, nx, ny);
+        int rc = launch_line_pass(inverse ? PASS_INV_ROWS : PASS_FWD_ROWS, p, nb, s);
+        if (rc != PSB_OK) return rc;
+        p.src = p.dst;
+        cols_geometry(p, nx, ny);
+        p.scale = scale;
+        rc = launch_line_pass(inverse ? PASS_INV_COLS : PASS_FWD_COLS, p, nb, s);
+        if (rc != PSB_OK) return rc;
+    }
+    return PSB_OK;
+}
+
+int psb_shift_probes(const psb_c64* base_k, const psb_c64* ramp_x, const psb_c64* ramp_y, int n_probes,
+                     int nx, int ny, psb_c64* out, void* stream) {
+    if (!base_k || !ramp_x || !ramp_y || !out || n_probes < 0 || nx < 1 || ny < 1)
+        return fail(PSB_ERR_INVALID, "psb_shift_probes: bad argument");
+    if (n_probes > 65535) return fail(PSB_ERR_UNSUPPORTED, "psb_shift_probes: more than 65535 probes");
+    cudaStream_t s = as_stream(stream);
+    const long long img = (long long)nx * ny;
+    PassParams p = base_params();
+    p.src = f2(base_k); p.dst = f2(out); p.src_img_stride = 0; p.dst_img_stride = img;
+    cols_geometry(p, nx, ny);
+    p.sep_p = f2(ramp_x); p.sep_img_stride_p = nx;    // along the line (kx)
+    p.sep_l = f2(ramp_y); p.sep_img_stride_l = ny;    // per line (ky)
+    int rc = launch_line_pass(PASS_CP, p, n_probes, s);
+    if (rc != PSB_OK) return rc;
+    p = base_params();
+    p.src = f2(out); p.dst = f2(out); p.src_img_stride = img; p.dst_img_stride = img;
+    rows_geometry(p, nx, ny);
+    p.scale = 1.0f / ((float)nx * (float)ny);
+    return launch_line_pass(PASS_INV_ROWS, p, n_probes, s);
+}
+
+int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_probes, int nz, int nx, int ny,
+                  const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out,
+                  long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
+                  void* stream) {
+    if (!probes || !t || !prop_x || !prop_y || !psi_work) return fail(PSB_ERR_INVALID, "psb_propagate: null pointer");
+    if (mode != 0 && mode != 1) return fail(PSB_ERR_INVALID, "psb_propagate: mode must be 0 or 1");
+    if (mode == 1 && !wf_out) return fail(PSB_ERR_INVALID, "psb_propagate: wf_out required in mode 1");
+    if (n_frames < 0 || n_probes < 1 || nz < 1 || nx < 1 || ny < 1 || layer_every < 0)
+        return fail(PSB_ERR_INVALID, "psb_propagate: bad sizes");
+    const long long n_img_ll = (long long)n_frames * n_probes;
+    if (n_img_ll == 0) return PSB_OK;
+    if (n_img_ll > 65535) return fail(PSB_ERR_UNSUPPORTED, "psb_propagate: frames*probes per call must be <= 65535");
+    const int n_img = (int)n_img_ll;
+    cudaStream_t s = as_stream(stream);
+    const long long img = (long long)nx * ny;
+
+    PassParams row = base_params();
+    row.dst = f2(psi_work); row.dst_img_stride = img;
+    rows_geometry(row, nx, ny);
+    row.mul_img_stride = (long long)nz * img;
+    row.mul_img_div = n_probes;
+
+    PassParams col = base_params();
+    col.src = f2(psi_work); col.dst = f2(psi_work); col.src_img_stride = img; col.dst_img_stride = img;
+    cols_geometry(col, nx, ny);
+    col.sep_p = f2(prop_x); col.sep_l = f2(prop_y);
+
+    PassParams ex = base_params();
+    ex.src = f2(psi_work); ex.src_img_stride = img;
+    cols_geometry(ex, nx, ny);
+    ex.probes = n_probes;
+    ex.out_stride_probe = stride_probe; ex.out_stride_frame = stride_frame;
+    ex.out_elem_stride = ny; ex.out_line_stride = 1;
+
+    int layer = 0;
+    for (int z = 0; z < nz; ++z) {
+        row.mul = f2(t) + (long long)z * img;
+        int rc;
+        if (z == 0) {
+            row.src = f2(probes); row.src_img_stride = img; row.src_img_mod = n_probes;
+            rc = launch_line_pass(PASS_R1, row, n_img, s);
+        } else {
+            row.src = f2(psi_work); row.src_img_stride = img; row.src_img_mod = 0;
+            rc = launch_line_pass(PASS_R, row, n_img, s);
+        }
+        if (rc != PSB_OK) return rc;
+        const bool last = z == nz - 1;
+        const bool tap = mode == 1 && (last || (layer_every > 0 && (z + 1) % layer_every == 0));
+        if (tap) {
+            ex.dst = f2(wf_out) + (long long)layer * stride_layer;
+            rc = launch_line_pass(PASS_CX, ex, n_img, s);
+            if (rc != PSB_OK) return rc;
+            ++layer;
+        }
+        if (!last) {
+            rc = launch_line_pass(PASS_C, col, n_img, s);
+            if (rc != PSB_OK) return rc;
+        }
+    }
+    if (mode == 0) {   // back to real space along y: psi is [x, ky] after the last row pass
+        PassParams inv = base_params();
+        inv.src = f2(psi_work); inv.dst = f2(psi_work); inv.src_img_stride = img; inv.dst_img_stride = img;
+        rows_geometry(inv, nx, ny);
+        inv.scale = 1.0f / (float)ny;
+        return launch_line_pass(PASS_INV_ROWS, inv, n_img, s);
+    }
+    return PSB_OK;
+}
+
+int psb_tacaw_intensity(const psb_c64* wf, long long stride_probe, long long stride_frame, int n_probes,
+                        int n_frames, long long npix, float* intensity, void* stream) {
+    if (!wf || !intensity || n_probes < 0 || n_frames < 1 || npix < 0) return fail(PSB_ERR_INVALID, "psb_tacaw_intensity: bad argument");
+    if (npix > 0x7fffffffLL) return fail(PSB_ERR_UNSUPPORTED, "psb_tacaw_intensity: npix too large");
+    if (n_probes > 65535) return fail(PSB_ERR_UNSUPPORTED, "psb_tacaw_intensity: more than 65535 probes");
+    PassParams p = base_params();
+    p.src = f2(wf); p.src_img_stride = stride_probe;
+    p.nlines = (int)npix; p.line_len = n_frames; p.line_stride = 1; p.elem_stride = stride_frame;
+    p.fout = intensity; p.dst_img_stride = (long long)n_frames * npix;
+    p.out_elem_stride = npix; p.out_line_stride = 1;
+    return launch_line_pass(PASS_TW, p, n_probes, as_stream(stream));
+}
+
+static int sum_pixels_impl(const float* in, const float2* cin, const float* mask, int rows, long long row_stride,
+                           long long npix, double* out, void* stream) {
+    if ((!in && !cin) || !out || rows < 0 || npix < 0) return fail(PSB_ERR_INVALID, "psb_sum_pixels: bad argument");
+    if (rows == 0) return PSB_OK;
+    SumPixParams p{in, cin, mask, row_stride, npix, out};
+    return go<SumPixels>(dim3(rows), SumPixels::kSmem, as_stream(stream), p, "sum_pixels");
+}
+
+int psb_sum_pixels(const float* in, const float* mask, int rows, long long row_stride, long long npix,
+                   double* out, void* stream) {
+    return sum_pixels_impl(in, nullptr, mask, rows, row_stride, npix, out, stream);
+}
+
+int psb_sum_abs_pixels(const psb_c64* in, const float* mask, int rows, long long row_stride, long long npix,
+                       double* out, void* stream) {
+    return sum_pixels_impl(nullptr, f2(in), mask, rows, row_stride, npix, out, stream);
+}
+
+int psb_sum_frames(const float* in, int groups, int n_frames, long long npix, float* out, void* stream) {
+    if (!in || !out || groups < 0 || n_frames < 1 || npix < 0) return fail(PSB_ERR_INVALID, "psb_sum_frames: bad argument");
+    if (groups == 0 || npix == 0) return PSB_OK;
+    if (groups > 65535) return fail(PSB_ERR_UNSUPPORTED, "psb_sum_frames: more than 65535 groups");
+    SumRowsParams p{in, n_frames, npix, out};
+    return go<SumRows>(dim3((unsigned)((npix + 255) / 256), groups), 0, as_stream(stream), p, "sum_frames");
+}
+
+}  // extern "C"

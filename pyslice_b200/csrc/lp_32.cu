@@ -1,0 +1,6 @@
+// line-pass kernels for N = 32 (E = 8 elements per thread; tile width rows 16 / cols 16)
+#define PSB_LP_N 32
+#define PSB_LP_E 8
+#define PSB_LP_WR 16
+#define PSB_LP_WC 16
+#include "line_pass_inst.cuh"

@@ -1,0 +1,251 @@
+"""Host-side driver of the CUDA engine: owns device buffers (torch tensors used purely as
+containers), frame-invariant tables, and the batching of frames / probes through libpsb.
+
+Nothing here computes on the CPU beyond the once-per-setup float64 tables of `hostmath`; every
+per-frame operation is a libpsb call on CUDA memory.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib, hostmath
+
+# Target size of the wave-function batch that is pushed through all slices at once.  Sized to stay
+# resident in B200's 126 MB L2 across the two passes of a slice step (DESIGN.md "L2 residency").
+PSI_BATCH_BYTES = 48 << 20
+# Upper bound for the transmission-function buffer of one frame batch.
+T_BATCH_BYTES = 24 << 30
+
+
+def _device(device=None) -> torch.device:
+    if _lib.is_emulated():                       # tests/emu only
+        return torch.device("cpu")
+    if not torch.cuda.is_available():
+        raise RuntimeError("pyslice_b200 requires a CUDA device (built for sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError(f"pyslice_b200 runs on CUDA devices only, got {device}")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _stream(device: torch.device) -> int:
+    if device.type != "cuda":
+        return 0
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _c64(x: np.ndarray, device) -> torch.Tensor:
+    return torch.from_numpy(np.ascontiguousarray(x).astype(np.complex64)).to(device)
+
+
+@dataclass
+class SlicePlan:
+    """Everything that does not change from frame to frame for one (box, sampling, voltage, types)."""
+    device: torch.device
+    xs: np.ndarray
+    ys: np.ndarray
+    zs: np.ndarray
+    nx: int
+    ny: int
+    nz: int
+    dx: float
+    dy: float
+    dz: float
+    eV: float
+    wavelength: float
+    sigma: float
+    type_Z: list                  # sorted unique atomic numbers
+    type_idx: torch.Tensor        # (A,) int32 on device
+    lo: torch.Tensor              # (nz,) float64 on device
+    hi: torch.Tensor
+    formfactors: torch.Tensor     # (ntypes, nx, ny) float32
+    prop_x: torch.Tensor          # (nx,) complex64, includes 1/(nx*ny)
+    prop_y: torch.Tensor          # (ny,) complex64
+    kxs: np.ndarray
+    kys: np.ndarray
+
+    @property
+    def ntypes(self) -> int:
+        return len(self.type_Z)
+
+
+def make_plan(xs, ys, zs, atom_kinds: Sequence, eV: float, device=None) -> SlicePlan:
+    device = _device(device)
+    xs = np.asarray(xs, dtype=np.float64)
+    ys = np.asarray(ys, dtype=np.float64)
+    zs = np.asarray(zs, dtype=np.float64)
+    nx, ny, nz = len(xs), len(ys), len(zs)
+    Z = np.array([hostmath.atomic_number(k) for k in atom_kinds], dtype=np.int64)
+    type_Z = sorted(set(Z.tolist()))
+    lut = {z: i for i, z in enumerate(type_Z)}
+    type_idx = np.array([lut[z] for z in Z.tolist()], dtype=np.int32)
+    lo, hi, dz = hostmath.slice_bounds(zs)
+    kxs, kys = hostmath.kgrid(xs, ys)
+    ff = hostmath.form_factor_table(kxs, kys, type_Z).astype(np.float32)
+    lam = hostmath.wavelength(eV)
+    px, py = hostmath.propagator_tables(kxs, kys, lam, dz)
+    px = px / (nx * ny)
+    return SlicePlan(
+        device=device, xs=xs, ys=ys, zs=zs, nx=nx, ny=ny, nz=nz, dx=float(xs[1] - xs[0]), dy=float(ys[1] - ys[0]),
+        dz=dz, eV=eV, wavelength=lam, sigma=hostmath.interaction_sigma(eV), type_Z=type_Z,
+        type_idx=torch.from_numpy(type_idx).to(device), lo=torch.from_numpy(lo).to(device),
+        hi=torch.from_numpy(hi).to(device), formfactors=torch.from_numpy(ff).to(device),
+        prop_x=_c64(px, device), prop_y=_c64(py, device), kxs=kxs, kys=kys)
+
+
+# --------------------------------------------------------------------------------------------
+def fft2(x: torch.Tensor, inverse: bool = False, scale: float = 1.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Batched 2-D FFT of a (..., nx, ny) complex64 tensor through psb_fft2 (unnormalised; `scale`
+    multiplies the result, pass 1/(nx*ny) for torch's ifft2 convention)."""
+    assert x.dtype == torch.complex64 and x.is_contiguous()
+    nx, ny = x.shape[-2:]
+    batch = x.numel() // (nx * ny)
+    if out is None:
+        out = torch.empty_like(x)
+    L = _lib.lib()
+    _lib.check(L.psb_fft2(x.data_ptr(), out.data_ptr(), batch, nx, ny, 1 if inverse else 0, scale, _stream(x.device)), "psb_fft2")
+    return out
+
+
+def bin_atoms(plan: SlicePlan, positions: torch.Tensor):
+    """positions (F, A, 3) float64 on device -> (offsets (F, nseg+1), atom_list, ux, uy (F, 2A))."""
+    F, A, _ = positions.shape
+    dev = plan.device
+    nseg = plan.nz * plan.ntypes
+    seg = torch.empty((F, A, 2), dtype=torch.int32, device=dev)
+    offsets = torch.empty((F, nseg + 1), dtype=torch.int32, device=dev)
+    atom_list = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
+    ux = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
+    uy = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
+    L = _lib.lib()
+    _lib.check(L.psb_bin_atoms(positions.data_ptr(), plan.type_idx.data_ptr(), F, A, plan.ntypes, plan.nz,
+                               plan.lo.data_ptr(), plan.hi.data_ptr(), plan.dz, plan.nx * plan.dx, plan.ny * plan.dy,
+                               seg.data_ptr(), offsets.data_ptr(), atom_list.data_ptr(), ux.data_ptr(), uy.data_ptr(),
+                               _stream(dev)), "psb_bin_atoms")
+    return offsets, atom_list, ux, uy
+
+
+def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential: bool = False,
+                       out: Optional[torch.Tensor] = None):
+    """positions (F, A, 3) float64 on device -> t (F, nz, nx, ny) complex64 [, V float32]."""
+    F, A, _ = positions.shape
+    dev = plan.device
+    offsets, _, ux, uy = bin_atoms(plan, positions)
+    t = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device=dev)
+    V = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev) if want_potential else None
+    scale = 1.0 / (plan.dx ** 2 * plan.dy ** 2)
+    L = _lib.lib()
+    _lib.check(L.psb_build_transmission(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
+                                        plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
+                                        t.data_ptr(), V.data_ptr() if V is not None else None, _stream(dev)),
+               "psb_build_transmission")
+    return (t, V) if want_potential else t
+
+
+def transmission_from_potential(V: torch.Tensor, sigma: float) -> torch.Tensor:
+    assert V.dtype == torch.float32 and V.is_contiguous()
+    t = torch.empty(V.shape, dtype=torch.complex64, device=V.device)
+    _lib.check(_lib.lib().psb_transmission_from_potential(V.data_ptr(), t.data_ptr(), V.numel(), sigma, _stream(V.device)),
+               "psb_transmission_from_potential")
+    return t
+
+
+def shift_probes(base_k: torch.Tensor, ramp_x: torch.Tensor, ramp_y: torch.Tensor) -> torch.Tensor:
+    """base_k (nx, ny), ramps (P, nx) / (P, ny) complex64 -> (P, nx, ny) shifted probes."""
+    P = ramp_x.shape[0]
+    nx, ny = base_k.shape
+    out = torch.empty((P, nx, ny), dtype=torch.complex64, device=base_k.device)
+    _lib.check(_lib.lib().psb_shift_probes(base_k.data_ptr(), ramp_x.data_ptr(), ramp_y.data_ptr(), P, nx, ny,
+                                           out.data_ptr(), _stream(base_k.device)), "psb_shift_probes")
+    return out
+
+
+def layer_count(nz: int, layer_every: int) -> int:
+    if layer_every <= 0:
+        return 1
+    return len([z for z in range(nz - 1) if (z + 1) % layer_every == 0]) + 1
+
+
+def propagate(plan: SlicePlan, probes: torch.Tensor, t: torch.Tensor, wf_out: Optional[torch.Tensor] = None,
+              frame0: int = 0, probe0: int = 0, layer_every: int = 0, work: Optional[torch.Tensor] = None):
+    """Push `probes` (P, nx, ny) through the transmission stack `t` (F, nz, nx, ny).
+
+    wf_out is None: returns the real-space exit waves (F, P, nx, ny)  (the reference's Propagate()).
+    wf_out (L, Ptot, Ttot, nx, ny): writes fftshift(fft2(exit)) for frames [frame0, frame0+F) and probes
+    [probe0, probe0+P) of every layer (the reference's per-frame worker + copy loop)."""
+    F = t.shape[0]
+    P = probes.shape[0]
+    nx, ny, nz = plan.nx, plan.ny, plan.nz
+    if work is None:
+        work = torch.empty((F * P, nx, ny), dtype=torch.complex64, device=plan.device)
+    L = _lib.lib()
+    if wf_out is None:
+        _lib.check(L.psb_propagate(probes.data_ptr(), t.data_ptr(), F, P, nz, nx, ny, plan.prop_x.data_ptr(),
+                                   plan.prop_y.data_ptr(), work.data_ptr(), 0, None, 0, 0, 0, 0, _stream(plan.device)),
+                   "psb_propagate")
+        return work.view(F, P, nx, ny)
+    Lr, Pt, Tt = wf_out.shape[:3]
+    assert wf_out.is_contiguous() and Lr == layer_count(nz, layer_every)
+    img = nx * ny
+    base = wf_out.data_ptr() + 8 * (probe0 * Tt * img + frame0 * img)
+    _lib.check(L.psb_propagate(probes.data_ptr(), t.data_ptr(), F, P, nz, nx, ny, plan.prop_x.data_ptr(),
+                               plan.prop_y.data_ptr(), work.data_ptr(), 1, base, Tt * img, img, Pt * Tt * img,
+                               layer_every, _stream(plan.device)), "psb_propagate")
+    return wf_out
+
+
+def tacaw_intensity(wf_layer: torch.Tensor) -> torch.Tensor:
+    """wf_layer (P, T, nx, ny) complex64 with contiguous (nx, ny) planes -> intensity (P, T, nx, ny) float32."""
+    P, T, nx, ny = wf_layer.shape
+    assert wf_layer.dtype == torch.complex64 and wf_layer.stride(3) == 1 and wf_layer.stride(2) == ny
+    out = torch.empty((P, T, nx, ny), dtype=torch.float32, device=wf_layer.device)
+    _lib.check(_lib.lib().psb_tacaw_intensity(wf_layer.data_ptr(), wf_layer.stride(0), wf_layer.stride(1), P, T,
+                                              nx * ny, out.data_ptr(), _stream(wf_layer.device)), "psb_tacaw_intensity")
+    return out
+
+
+def sum_pixels(x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x (rows, npix) float32 or complex64 (|z| is summed), contiguous rows -> (rows,) float64."""
+    rows, npix = x.shape
+    assert x.stride(1) == 1
+    out = torch.empty((rows,), dtype=torch.float64, device=x.device)
+    m = mask.data_ptr() if mask is not None else None
+    L = _lib.lib()
+    fn = L.psb_sum_abs_pixels if x.dtype == torch.complex64 else L.psb_sum_pixels
+    assert x.dtype in (torch.complex64, torch.float32)
+    _lib.check(fn(x.data_ptr(), m, rows, x.stride(0), npix, out.data_ptr(), _stream(x.device)), "psb_sum_pixels")
+    return out
+
+
+def sum_frames(x: torch.Tensor) -> torch.Tensor:
+    """x (G, T, npix) float32 contiguous -> (G, npix) float32 sums over T."""
+    G, T, npix = x.shape
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = torch.empty((G, npix), dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().psb_sum_frames(x.data_ptr(), G, T, npix, out.data_ptr(), _stream(x.device)), "psb_sum_frames")
+    return out
+
+
+def batch_sizes(plan: SlicePlan, n_probes: int, n_frames: int):
+    """(frames per batch, probes per sub-batch) so the psi batch stays L2-resident and the
+    transmission buffer stays bounded."""
+    img = plan.nx * plan.ny * 8
+    per_frame_t = plan.nz * img
+    max_imgs = max(1, PSI_BATCH_BYTES // img)
+    if n_probes >= max_imgs:
+        fb, pb = 1, max_imgs
+    else:
+        fb, pb = max(1, max_imgs // n_probes), n_probes
+    fb = min(fb, max(1, T_BATCH_BYTES // per_frame_t), max(1, 65535 // plan.nz), n_frames)
+    if plan.device.type == "cuda":
+        free, _ = torch.cuda.mem_get_info(plan.device)
+        fb = max(1, min(fb, int(free * 0.5) // per_frame_t))
+    return fb, min(pb, 65535 // max(1, fb))

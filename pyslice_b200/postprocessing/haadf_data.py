@@ -1,0 +1,50 @@
+"""`HAADFData(wfdata).calculateADF()`: annular dark-field signal from the exit waves
+(reference src/postprocessing/haadf_data.py:35-72), detector sum on the GPU."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from .. import engine
+from .wf_data import WFData
+
+
+class HAADFData(WFData):
+    def __init__(self, WFData):
+        self.__class__ = type(WFData.__class__.__name__, (self.__class__, WFData.__class__), {})
+        self.__dict__ = WFData.__dict__
+
+    def calculateADF(self, collection_angle: float = 45, preview: bool = False):
+        """adf[i, j] = mean_frames sum_k |psi_k| * (|k| > collection_angle*1e-3/lambda) for the probe
+        nearest to the i-th unique x / j-th unique y (haadf_data.py:43-65).  The mask uses the
+        float32 kxs/kys labels of the WFData, like the reference."""
+        pp = np.asarray(self.probe_positions)
+        self.xs = torch.as_tensor(sorted(set(pp[:, 0])))
+        self.ys = torch.as_tensor(sorted(set(pp[:, 1])))
+        kxs = torch.as_tensor(self.kxs)
+        kys = torch.as_tensor(self.kys)
+        q = torch.sqrt(kxs[:, None] ** 2 + kys[None, :] ** 2)
+        radius = (collection_angle * 1e-3) / self.probe.wavelength
+        mask = torch.zeros(q.shape)
+        mask[q > radius] = 1
+        wf = self.wavefunction_data[:, :, :, :, -1]
+        if not hasattr(wf, "dim"):
+            wf = torch.from_numpy(np.asarray(wf))
+        dev = engine._device(wf.device if wf.device.type == "cuda" else None)
+        wf = wf.to(device=dev, dtype=torch.complex64).contiguous()
+        P, T, nx, ny = wf.shape
+        sums = engine.sum_pixels(wf.reshape(P * T, nx * ny), mask.to(dev, torch.float32).reshape(-1))
+        per_probe = sums.reshape(P, T).mean(dim=1).cpu()
+        self.adf = torch.zeros((len(self.xs), len(self.ys)))
+        for i, x in enumerate(self.xs.tolist()):
+            for j, y in enumerate(self.ys.tolist()):
+                p = int(np.argmin(np.sqrt(np.sum((pp - np.array([x, y])[None, :]) ** 2, axis=1))))
+                self.adf[i, j] = per_probe[p]
+        return self.adf
+
+    def plot(self):
+        import matplotlib.pyplot as plt
+        fig, ax = plt.subplots()
+        ax.imshow(self.adf.T, cmap="inferno",
+                  extent=(float(self.xs.min()), float(self.xs.max()), float(self.ys.min()), float(self.ys.max())))
+        plt.show()
