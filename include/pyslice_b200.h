@@ -40,6 +40,8 @@ const char* psb_last_error(void);
 int psb_sm_count(void);
 /* drop cached FFT tables of all devices */
 void psb_release_tables(void);
+/* kernels launched by this library in this process so far (benchmark bookkeeping) */
+long long psb_launch_count(void);
 
 /* ---- atom -> slice binning: src/multislice/potentials.py:297-317 (+ bounds :304-305) -------------
  * positions (F, A, 3) float64; type_idx (A) dense type index in [0, ntypes);

@@ -58,6 +58,7 @@ int psb_version(void) { return 100; }
 const char* psb_last_error(void) { return last_error(); }
 int psb_sm_count(void) { return rt::sm_count(); }
 void psb_release_tables(void) { free_all_tables(); }
+long long psb_launch_count(void) { return launch_counter(); }
 
 int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames, int n_atoms, int ntypes,
                   int nz, const double* lo, const double* hi, double dz, double lx_eff, double ly_eff,

@@ -21,7 +21,7 @@
 namespace psb {
 
 // largest supported power-of-two line size
-constexpr int kMaxLine = 4096;
+constexpr int kMaxLine = 8192;
 
 constexpr float kC1 = 0.92387953251128674f;   // cos(pi/8)
 constexpr float kS1 = 0.38268343236508977f;   // sin(pi/8)
@@ -133,6 +133,7 @@ PSB_PLAN(512, 16, 3, 16, 2, 16, 1)
 PSB_PLAN(1024, 16, 3, 16, 4, 16, 1)
 PSB_PLAN(2048, 16, 3, 16, 8, 16, 1)
 PSB_PLAN(4096, 16, 3, 16, 16, 16, 1)
+PSB_PLAN(8192, 16, 4, 16, 2, 16, 16)
 #undef PSB_PLAN
 
 // Shared-memory addressing of position q of line c inside a tile of W lines.

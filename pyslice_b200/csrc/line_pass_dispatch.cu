@@ -4,7 +4,7 @@
 namespace psb {
 
 #define PSB_DECL(N) int launch_lp_##N(int kind, bool blue, const PassParams& p, int n_img, cudaStream_t s);
-PSB_DECL(16) PSB_DECL(32) PSB_DECL(64) PSB_DECL(128) PSB_DECL(256) PSB_DECL(512) PSB_DECL(1024) PSB_DECL(2048) PSB_DECL(4096)
+PSB_DECL(16) PSB_DECL(32) PSB_DECL(64) PSB_DECL(128) PSB_DECL(256) PSB_DECL(512) PSB_DECL(1024) PSB_DECL(2048) PSB_DECL(4096) PSB_DECL(8192)
 #undef PSB_DECL
 
 int launch_line_pass(int kind, PassParams p, int n_img, cudaStream_t stream) {
@@ -24,6 +24,7 @@ int launch_line_pass(int kind, PassParams p, int n_img, cudaStream_t stream) {
         case 1024: return launch_lp_1024(kind, blue, p, n_img, stream);
         case 2048: return launch_lp_2048(kind, blue, p, n_img, stream);
         case 4096: return launch_lp_4096(kind, blue, p, n_img, stream);
+        case 8192: return launch_lp_8192(kind, blue, p, n_img, stream);
     }
     return fail(PSB_ERR_UNSUPPORTED, "unsupported FFT size");
 }

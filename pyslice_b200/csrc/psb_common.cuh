@@ -46,6 +46,12 @@ static inline float __int2float_rn(int v) { return (float)v; }
 
 namespace psb {
 
+// number of kernel launches issued by this library (bench.py reports it as gpu_launches)
+inline long long& launch_counter() {
+    static long long n = 0;
+    return n;
+}
+
 // ---- complex helpers (float2 = complex64) -------------------------------------------------
 PSB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 PSB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -94,6 +100,7 @@ inline cudaError_t launch(dim3 grid, size_t smem, cudaStream_t stream, const P& 
         }
     }
     psb_kernel<K, P><<<grid, K::kThreads, smem, stream>>>(p);
+    ++launch_counter();
     return cudaGetLastError();
 }
 #else

@@ -77,7 +77,7 @@ int fft_size_for(int n, bool* bluestein) {
 int get_fft_tables(int n, FftTables* out, int* N_out, bool* blue_out, cudaStream_t s) {
     bool blue = false;
     int N = fft_size_for(n, &blue);
-    if (N == 0) return fail(PSB_ERR_UNSUPPORTED, "FFT length " + std::to_string(n) + " not supported (max 4096, or 2048 if not a power of two)");
+    if (N == 0) return fail(PSB_ERR_UNSUPPORTED, "FFT length " + std::to_string(n) + " not supported (max 8192, or 4096 if not a power of two)");
     std::lock_guard<std::mutex> lk(g_mu);
     const int dev = rt::device();
     auto key = std::make_pair(dev, n);

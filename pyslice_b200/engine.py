@@ -21,6 +21,59 @@ PSI_BATCH_BYTES = 48 << 20
 T_BATCH_BYTES = 24 << 30
 
 
+class PhaseTimer:
+    """Optional CUDA-event timing of the pipeline phases on the launching stream (used by bench.py to
+    report the slice-step kernel's own duration).  `with timer.phase("propagate"): ...` records an
+    event pair; `totals()` synchronises and returns milliseconds per phase."""
+
+    def __init__(self, device):
+        self.device = device
+        self.pairs = []
+
+    class _Span:
+        def __init__(self, owner, name):
+            self.owner, self.name = owner, name
+
+        def __enter__(self):
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record(torch.cuda.current_stream(self.owner.device))
+
+        def __exit__(self, *exc):
+            self.b.record(torch.cuda.current_stream(self.owner.device))
+            self.owner.pairs.append((self.name, self.a, self.b))
+
+    def phase(self, name):
+        return PhaseTimer._Span(self, name)
+
+    def totals(self):
+        torch.cuda.synchronize(self.device)
+        out = {}
+        for name, a, b in self.pairs:
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+        self.pairs = []
+        return out
+
+
+class _NoTimer:
+    class _Null:
+        def __enter__(self):
+            return None
+
+        def __exit__(self, *exc):
+            return False
+
+    def phase(self, name):
+        return _NoTimer._Null()
+
+
+NO_TIMER = _NoTimer()
+
+
+def launch_count() -> int:
+    return int(_lib.lib().psb_launch_count())
+
+
 def _device(device=None) -> torch.device:
     if _lib.is_emulated():                       # tests/emu only
         return torch.device("cpu")

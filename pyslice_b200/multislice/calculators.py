@@ -132,8 +132,11 @@ class MultisliceCalculator:
             return 0, self.n_frames
         return self.shard.start, self.shard.start + self.shard.counts[self.shard.rank]
 
-    def run(self) -> WFData:
+    def run(self, timer=None) -> WFData:
+        """Propagate every probe through every frame (reference calculators.py:163-250).
+        `timer`: optional engine.PhaseTimer collecting CUDA-event times per phase."""
         t_start = time.time()
+        timer = timer or engine.NO_TIMER
         plan = self._plan
         f_lo, f_hi = self._local_frames()
         T_loc = f_hi - f_lo
@@ -145,13 +148,19 @@ class MultisliceCalculator:
         positions = self.trajectory.positions
         for b0 in range(0, T_loc, fb):
             nb = min(fb, T_loc - b0)
-            pos = np.ascontiguousarray(positions[f_lo + b0:f_lo + b0 + nb], dtype=np.float64)
-            pos_d = torch.from_numpy(pos).to(self.device, non_blocking=True)
-            t = engine.build_transmission(plan, pos_d, out=tbuf[:nb])
-            for p0 in range(0, P, pb):
-                np_ = min(pb, P - p0)
-                engine.propagate(plan, self._probes[p0:p0 + np_], t, wf_out=store, frame0=b0, probe0=p0,
-                                 layer_every=self.layer_every, work=work)
+            block = positions[f_lo + b0:f_lo + b0 + nb]
+            if isinstance(block, torch.Tensor):      # already resident (device arm of bench.py)
+                pos_d = block.to(device=self.device, dtype=torch.float64).contiguous()
+            else:
+                pos = np.ascontiguousarray(block, dtype=np.float64)
+                pos_d = torch.from_numpy(pos).to(self.device, non_blocking=True)
+            with timer.phase("potential"):
+                t = engine.build_transmission(plan, pos_d, out=tbuf[:nb])
+            with timer.phase("propagate"):
+                for p0 in range(0, P, pb):
+                    np_ = min(pb, P - p0)
+                    engine.propagate(plan, self._probes[p0:p0 + np_], t, wf_out=store, frame0=b0, probe0=p0,
+                                     layer_every=self.layer_every, work=work)
         # (L, P, T, nx, ny) storage exposed in the reference's (P, T, nx, ny, L) index order
         self.wavefunction_data = store.permute(1, 2, 3, 4, 0)
         logger.info(f"Simulation completed in {time.time() - t_start:.2f}s ({T_loc} frames computed)")

@@ -1,0 +1,298 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path through the C ABI against
+the CPU oracle and the reference goldens.
+
+Tolerances (BASELINE.json north_star): atom->slice binning bit-exact; exit wave relative L2 <= 1e-4
+per (probe, frame); TACAW intensity <= 1e-3 relative; potential <= 1e-5 (own budget)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pyslice_oracle as orc
+from tests.helpers import golden, rel_l2, si_c1_traj, small64_traj, tacaw48_traj
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def real_library():
+    from pyslice_b200 import _lib
+    _lib._reset()
+    assert not _lib.is_emulated()
+    yield
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def membership(plan, offsets, atom_list, n_atoms):
+    off, al = offsets.cpu().numpy(), atom_list.cpu().numpy()
+    m = np.zeros((plan.nz, n_atoms), dtype=bool)
+    for s in range(plan.nz):
+        for t in range(plan.ntypes):
+            seg = s * plan.ntypes + t
+            ids = al[off[seg]:off[seg + 1]]
+            assert np.all(np.diff(ids) > 0)
+            m[s, ids] = True
+    return m
+
+
+FFT_SHAPES = [(16, 16), (32, 64), (64, 64), (128, 256), (256, 256), (512, 512), (1024, 1024), (2048, 64),
+              (64, 4096), (8192, 16), (48, 40), (20, 36), (272, 272), (100, 500), (1000, 24), (24, 2000), (4000, 16),
+              (1, 64), (64, 1), (7, 9)]
+
+
+@pytest.mark.parametrize("shape", FFT_SHAPES)
+def test_fft2_every_size(shape):
+    from pyslice_b200 import engine
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn((3,) + shape, dtype=torch.complex64, device="cuda", generator=g)
+    ref = torch.fft.fft2(x.to(torch.complex128))
+    got = engine.fft2(x)
+    assert float((got - ref).norm() / ref.norm()) < 2e-6
+    refi = torch.fft.ifft2(x.to(torch.complex128))
+    goti = engine.fft2(x, inverse=True, scale=1.0 / (shape[0] * shape[1]))
+    assert float((goti - refi).norm() / refi.norm()) < 2e-6
+
+
+def test_binning_bit_exact_small_and_large():
+    from pyslice_b200 import engine, hostmath, synthetic
+    traj = small64_traj()
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    offsets, atom_list, _, _ = engine.bin_atoms(plan, dev(traj.positions))
+    for f in range(traj.n_frames):
+        assert np.array_equal(membership(plan, offsets[f], atom_list[f], traj.n_atoms),
+                              orc.bin_atoms(traj.positions[f][:, 2], zs))
+    # 611 slices with 1-ulp gaps/overlaps (lz = 305.3), 20k atoms incl. atoms on every slice bound
+    big = synthetic.random_trajectory(n_atoms=20000, box=(6.35, 6.35, 305.3), n_frames=2, seed=9, stray=True)
+    xs, ys, zs, *_ = hostmath.grid_from_box(big.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, big.atom_types.tolist(), 100e3)
+    offsets, atom_list, _, _ = engine.bin_atoms(plan, dev(big.positions))
+    for f in range(2):
+        want = orc.bin_atoms(big.positions[f][:, 2], zs)
+        got = membership(plan, offsets[f], atom_list[f], big.n_atoms)
+        assert np.array_equal(got, want)
+        assert (want.sum(axis=0) == 2).any() or (want.sum(axis=0) == 0).any()
+
+
+def test_potential_against_reference_golden():
+    from pyslice_b200 import engine, hostmath
+    traj = small64_traj()
+    g = golden("small64.npz")
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    t, V = engine.build_transmission(plan, dev(traj.positions[:1]), want_potential=True)
+    assert rel_l2(V[0].permute(1, 2, 0).cpu().numpy(), g["potential0"]) < 1e-5
+    assert float((t.abs() - 1).abs().max()) < 1e-6            # unit-modulus transmission
+
+
+def test_small64_runs_against_reference_golden():
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    from pyslice_b200.postprocessing.haadf_data import HAADFData
+    traj = small64_traj()
+    g = golden("small64.npz")
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=0.0, voltage_eV=100e3)
+    wf = calc.run()
+    assert tuple(wf.wavefunction_data.shape) == g["wf_plane"].shape
+    for f in range(3):
+        assert rel_l2(wf.wavefunction_data[0, f, :, :, 0].cpu().numpy(), g["wf_plane"][0, f, :, :, 0]) < 1e-4
+    assert np.array_equal(wf.kxs.numpy(), g["kxs"]) and np.array_equal(wf.time, g["time"])
+    calc.setup(traj, aperture=30.0, voltage_eV=100e3, probe_positions=g["probe_xy"])
+    assert rel_l2(calc.base_probe.array.cpu().numpy(), g["base_probe"]) < 1e-5
+    wf2 = calc.run()
+    for p in range(4):
+        for f in range(3):
+            assert rel_l2(wf2.wavefunction_data[p, f, :, :, 0].cpu().numpy(), g["wf_probes"][p, f, :, :, 0]) < 1e-4
+    adf = HAADFData(wf2).calculateADF(45)
+    assert rel_l2(adf.numpy(), g["adf"]) < 1e-4
+
+
+def test_tacaw48_against_reference_golden():
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    from pyslice_b200.postprocessing.tacaw_data import TACAWData
+    traj = tacaw48_traj()
+    g = golden("tacaw48.npz")
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=0.0, voltage_eV=100e3)
+    wf = calc.run()
+    assert rel_l2(wf.wavefunction_data.cpu().numpy(), g["wf"]) < 1e-4
+    tac = TACAWData(wf)
+    inten = tac.intensity.cpu().numpy()
+    dc = inten.shape[1] // 2
+    keep = [i for i in range(inten.shape[1]) if i != dc]
+    assert rel_l2(inten[:, keep], g["intensity"][:, keep]) < 1e-3
+    assert inten[:, dc].max() < 1e-9 * inten.max()             # reference DC bin ~1e-19: absolute check
+    assert rel_l2(tac.spectrum()[keep], g["spectrum"][keep]) < 1e-3
+    assert rel_l2(tac.spectrum(0)[keep], g["spectrum0"][keep]) < 1e-3
+    assert rel_l2(tac.diffraction(), g["diffraction"]) < 1e-3
+    assert rel_l2(tac.spectral_diffraction(20.0), g["spectral_diffraction"]) < 1e-3
+    assert rel_l2(tac.spectrum_image(20.0), g["spectrum_image"]) < 1e-3
+    assert rel_l2(tac.dispersion(g["kx_path"], g["ky_path"])[keep], g["dispersion"][keep]) < 1e-3
+    ref_masked = (g["intensity"] * g["mask"][None, None]).sum(axis=(2, 3)).mean(axis=0)
+    assert rel_l2(tac.masked_spectrum(g["mask"])[keep], ref_masked[keep]) < 1e-3
+
+
+def test_si_c1_against_reference_golden():
+    """config C1 geometry: 256 x 256 x 103, 2000 Si atoms, plane wave."""
+    from pyslice_b200 import engine
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    g = golden("si_c1.npz")
+    traj = si_c1_traj()
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=0.0, voltage_eV=100e3)
+    assert (calc.nx, calc.ny, calc.nz) == (256, 256, 103)
+    wf = calc.run()
+    assert rel_l2(wf.wavefunction_data[0, 0, :, :, 0].cpu().numpy(), g["wf"]) < 1e-4
+    _, V = engine.build_transmission(calc._plan, dev(traj.positions[:1]), want_potential=True)
+    V = V[0].permute(1, 2, 0).cpu().numpy()
+    assert rel_l2(V[:, :, [0, 1, 51, 102]], g["pot_planes"]) < 1e-5
+    assert rel_l2(V.sum(axis=2), g["pot_sum_z"]) < 1e-5
+
+
+@pytest.mark.parametrize("aperture", [0.0, 30.0])
+def test_long_stack_611_slices_vs_oracle(aperture):
+    """fp32 round-off accumulates over slices: check at nz = 611."""
+    from pyslice_b200 import synthetic
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    traj = synthetic.random_trajectory(n_atoms=6000, box=(12.75, 12.75, 305.3), n_frames=1, seed=21, types=(14,))
+    pp = None if aperture == 0 else [(3.0, 4.0), (7.7, 9.1)]
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=aperture, voltage_eV=100e3, probe_positions=pp)
+    assert (calc.nx, calc.nz) == (128, 611)
+    wf = calc.run().wavefunction_data.cpu().numpy()
+    ref, _ = orc.multislice_run(traj.positions, traj.atom_types, traj.box_matrix, aperture=aperture,
+                                voltage_eV=100e3, probe_positions=pp, workers=4)
+    for p in range(wf.shape[0]):
+        assert rel_l2(wf[p, 0], ref[p, 0]) < 1e-4
+
+
+def test_non_power_of_two_grid_272_vs_oracle():
+    """natural Si lattice constant -> 272 x 272 grid (Bluestein path), config C1 variant."""
+    from pyslice_b200 import synthetic
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    traj = synthetic.silicon_trajectory(cells=(5, 5, 4), a=5.431, n_frames=2, seed=4)
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=0.0, voltage_eV=100e3)
+    assert (calc.nx, calc.ny) == (272, 272)
+    wf = calc.run().wavefunction_data.cpu().numpy()
+    ref, _ = orc.multislice_run(traj.positions, traj.atom_types, traj.box_matrix, voltage_eV=100e3, workers=4)
+    for f in range(2):
+        assert rel_l2(wf[0, f], ref[0, f]) < 1e-4
+
+
+def test_hbn_multi_type_probes_vs_oracle():
+    """three element types, empty slices, convergent probes (config C3 physics at 128 x 128)."""
+    from pyslice_b200 import synthetic
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    from pyslice_b200.multislice.multislice import probe_grid
+    traj = synthetic.hbn_graphene_trajectory(cells=(5, 3), n_layers=4, n_frames=2, seed=2)
+    xy = probe_grid([2, 9], [3, 10], 3, 2)
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=30.0, voltage_eV=100e3, probe_positions=xy)
+    wf = calc.run().wavefunction_data.cpu().numpy()
+    ref, _ = orc.multislice_run(traj.positions, traj.atom_types, traj.box_matrix, aperture=30.0, voltage_eV=100e3,
+                                probe_positions=xy, workers=4)
+    assert wf.shape == ref.shape
+    for p in range(6):
+        for f in range(2):
+            assert rel_l2(wf[p, f], ref[p, f]) < 1e-4
+
+
+@pytest.mark.parametrize("T", [20, 100, 500, 2000, 4000, 64])
+def test_tacaw_time_fft_lengths(T):
+    from pyslice_b200 import engine
+    rng = np.random.default_rng(T)
+    P, nx, ny = 2, 8, 16
+    base = rng.normal(size=(P, 1, nx, ny)) + 1j * rng.normal(size=(P, 1, nx, ny))
+    x = (5.0 * base + 0.1 * (rng.normal(size=(P, T, nx, ny)) + 1j * rng.normal(size=(P, T, nx, ny)))).astype(np.complex64)
+    got = engine.tacaw_intensity(dev(x)).cpu().numpy()
+    ref, _ = orc.tacaw_intensity(x.astype(np.complex128), np.arange(T) * 0.01)
+    dc = T // 2
+    keep = [i for i in range(T) if i != dc]
+    assert rel_l2(got[:, keep], ref[:, keep]) < 1e-3
+    # Parseval: sum_w I = T * sum_t |psi - mean|^2
+    d = x.astype(np.complex128) - x.astype(np.complex128).mean(axis=1, keepdims=True)
+    assert abs(got.sum() / (T * (np.abs(d) ** 2).sum()) - 1) < 1e-4
+
+
+def test_full_size_properties_c2_grid():
+    """Size-independent properties at the benchmark grid (256 x 256 x 512, 10k atoms, 2 frames):
+    |t| = 1, the propagator is unitary so sum|wf|^2 = nx*ny*sum|probe|^2, and runs are deterministic."""
+    from pyslice_b200 import engine, synthetic
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    traj = synthetic.silicon_trajectory(cells=(5, 5, 50), a=5.11, n_frames=2, seed=1, displacement="phonon")
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=0.0, voltage_eV=100e3)
+    assert (calc.nx, calc.ny, calc.nz) == (256, 256, 512)
+    wf1 = calc.run().wavefunction_data.clone()
+    wf2 = calc.run().wavefunction_data
+    assert torch.equal(wf1, wf2)
+    power = (wf1.abs().double() ** 2).sum(dim=(2, 3, 4)) / (256 * 256)
+    assert float((power / (256 * 256) - 1).abs().max()) < 1e-4
+    # batching must not change a single bit
+    old = engine.PSI_BATCH_BYTES
+    try:
+        engine.PSI_BATCH_BYTES = 600 << 10
+        wf3 = calc.run().wavefunction_data
+    finally:
+        engine.PSI_BATCH_BYTES = old
+    assert torch.equal(wf1, wf3)
+    # one frame against the oracle at full depth
+    ref, _ = orc.multislice_run(traj.positions[:1], traj.atom_types, traj.box_matrix, voltage_eV=100e3, workers=8)
+    assert rel_l2(wf1[0, 0, :, :, 0].cpu().numpy(), ref[0, 0, :, :, 0]) < 1e-4
+
+
+def test_layers_and_low_level_api():
+    from pyslice_b200 import hostmath
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    from pyslice_b200.multislice.multislice import Probe, Propagate, create_batched_probes
+    from pyslice_b200.multislice.potentials import Potential
+    traj = small64_traj().slice_timesteps([0])
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=0.0, voltage_eV=100e3, layer_every=4)
+    wf = calc.run()
+    assert list(wf.layer) == [3, 7, 8]
+    V = orc.potential(xs, ys, zs, traj.positions[0], traj.atom_types)
+    for li, last in enumerate([3, 7, 8]):
+        ref = orc.exit_to_kspace(orc.propagate(np.ones((64, 64)), V, xs, ys, zs, 100e3, n_slices=last + 1))[0]
+        assert rel_l2(wf.wavefunction_data[0, 0, :, :, li].cpu().numpy(), ref) < 1e-4
+    pot = Potential(xs, ys, zs, traj.positions[0], traj.atom_types.tolist())
+    assert rel_l2(pot.array.cpu().numpy(), V) < 1e-5
+    base = Probe(xs, ys, 30.0, 100e3)
+    probes = create_batched_probes(base, [(1.0, 2.0), (3.3, 4.4)])
+    want = orc.shifted_probes(orc.probe_array(xs, ys, 30.0, 100e3), xs, ys, [(1.0, 2.0), (3.3, 4.4)])
+    assert rel_l2(probes.array.cpu().numpy(), want) < 1e-5
+    psi = Propagate(probes, pot)
+    ref = orc.propagate(want, V, xs, ys, zs, 100e3)
+    assert rel_l2(psi.cpu().numpy(), ref) < 1e-4
+    # defocus (reference multislice.py:183-190)
+    p2 = Probe(xs, ys, 30.0, 100e3)
+    p2.defocus(200.0)
+    k = np.fft.fftfreq(64, xs[1] - xs[0])
+    Pd = np.exp(-1j * np.pi * orc.wavelength(100e3) * 200.0 * (k[:, None] ** 2 + k[None, :] ** 2))
+    wantd = np.fft.ifft2(Pd * np.fft.fft2(orc.probe_array(xs, ys, 30.0, 100e3)))
+    assert rel_l2(p2.array.cpu().numpy(), wantd) < 1e-5
+
+
+def test_probe_kat():
+    """the reference's own probe recipe (src/unittests/00_probe.py:7-18), 501 x 491 grid"""
+    from pyslice_b200.multislice.multislice import Probe
+    g = golden("probe_kat.npz")
+    xs = np.linspace(0, 50, 501)
+    ys = np.linspace(0, 49, 491)
+    for mrad in (1, 5, 30):
+        p = Probe(xs, ys, mrad, 100e3).array.cpu().numpy()[::5, ::5]
+        assert rel_l2(p, g[f"mrad{mrad}"]) < 1e-5
+
+
+def test_errors_are_loud():
+    from pyslice_b200 import _lib, engine
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    with pytest.raises(RuntimeError):
+        MultisliceCalculator(force_cpu=True)
+    x = torch.zeros((1, 3, 9000), dtype=torch.complex64, device="cuda")
+    with pytest.raises(_lib.PsbError):
+        engine.fft2(x)                      # 9000 > 4096 and not a power of two -> unsupported
