@@ -58,10 +58,14 @@ int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames
 /* ---- projected potential -> transmission: potentials.py:319-342 and multislice.py:281-282 --------
  * formfactors (ntypes, nx, ny) float32 = Kirkland f_e on the fftfreq grid (host table, potentials.py:86-96).
  * t_out (F, nz, nx, ny) complex64 = exp(i*sigma*V), V = Re IFFT2(S) * scale  with scale = 1/(dx^2 dy^2)
- * (the 1/(nx*ny) of the inverse FFT is applied internally).  v_out (same shape, float32) optional. */
+ * (the 1/(nx*ny) of the inverse FFT is applied internally).  v_out (same shape, float32) optional.
+ * scratch: complex64 workspace of scratch_elems >= ((nz+1)/2)*nx*ny elements (one frame); frames are
+ * processed in chunks that fit it.  V is real, so two slices share one complex inverse FFT and only
+ * half of each spectrum is summed (the Hermitian part -- exactly what the reference's Re() keeps). */
 int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
                            int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
-                           float scale, float sigma, psb_c64* t_out, float* v_out, void* stream);
+                           float scale, float sigma, psb_c64* t_out, float* v_out, psb_c64* scratch,
+                           long long scratch_elems, void* stream);
 
 /* t = exp(i*sigma*V) for a user-supplied real potential (Propagate() on a Potential object) */
 int psb_transmission_from_potential(const float* v, psb_c64* t, long long n, float sigma, void* stream);

@@ -91,32 +91,54 @@ int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames
 
 int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
                            int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
-                           float scale, float sigma, psb_c64* t_out, float* v_out, void* stream) {
-    if (!offsets || !ux || !uy || !formfactors || !t_out) return fail(PSB_ERR_INVALID, "psb_build_transmission: null pointer");
+                           float scale, float sigma, psb_c64* t_out, float* v_out, psb_c64* scratch,
+                           long long scratch_elems, void* stream) {
+    if (!offsets || !ux || !uy || !formfactors || !t_out || !scratch)
+        return fail(PSB_ERR_INVALID, "psb_build_transmission: null pointer");
     if (n_frames < 0 || nz < 1 || nx < 1 || ny < 1 || ntypes < 1) return fail(PSB_ERR_INVALID, "psb_build_transmission: bad sizes");
     if (n_frames == 0) return PSB_OK;
-    if (nz > 65535 || n_frames > 65535 || (long long)n_frames * nz > 65535)
-        return fail(PSB_ERR_UNSUPPORTED, "psb_build_transmission: frames*slices per call must be <= 65535");
     cudaStream_t s = as_stream(stream);
-    SfParams sp;
-    sp.offsets = offsets; sp.ux = ux; sp.uy = uy; sp.cap = 2 * n_atoms; sp.nz = nz; sp.ntypes = ntypes;
-    sp.nx = nx; sp.ny = ny; sp.ff = formfactors; sp.out = f2(t_out);
-    const int T = StructureFactor::TILE;
-    dim3 grid(((nx + T - 1) / T) * ((ny + T - 1) / T), nz, n_frames);
-    int rc = go<StructureFactor>(grid, StructureFactor::kSmem, s, sp, "structure_factor");
-    if (rc != PSB_OK) return rc;
-
     const long long img = (long long)nx * ny;
-    PassParams p = base_params();
-    p.src = f2(t_out); p.dst = f2(t_out); p.src_img_stride = img; p.dst_img_stride = img;
-    cols_geometry(p, nx, ny);
-    rc = launch_line_pass(PASS_INV_COLS, p, n_frames * nz, s);
-    if (rc != PSB_OK) return rc;
-    rows_geometry(p, nx, ny);
-    p.scale = scale / ((float)nx * (float)ny);
-    p.sigma = sigma;
-    p.vout = v_out;
-    return launch_line_pass(PASS_RI, p, n_frames * nz, s);
+    const int npairs = (nz + 1) / 2;
+    if (npairs > 65535) return fail(PSB_ERR_UNSUPPORTED, "psb_build_transmission: too many slices");
+    long long chunk = scratch_elems / (npairs * img);          // frames per chunk that fit the scratch
+    if (chunk < 1) return fail(PSB_ERR_INVALID, "psb_build_transmission: scratch smaller than one frame ((nz+1)/2*nx*ny elements)");
+    if (chunk > 65535 / npairs) chunk = 65535 / npairs;         // grid.y limit of the line passes
+    if (chunk < 1) chunk = 1;
+    const int nseg = nz * ntypes;
+    const int TXs = StructureFactorPaired::TX, TYs = StructureFactorPaired::TY;
+    const int tiles = ((nx + TXs - 1) / TXs) * ((ny / 2 + 1 + TYs - 1) / TYs);
+    for (long long f0 = 0; f0 < n_frames; f0 += chunk) {
+        const int nf = (int)(n_frames - f0 < chunk ? n_frames - f0 : chunk);
+        SfPairParams sp;
+        sp.offsets = offsets + f0 * (nseg + 1); sp.ux = ux + f0 * 2 * n_atoms; sp.uy = uy + f0 * 2 * n_atoms;
+        sp.cap = 2 * n_atoms; sp.nz = nz; sp.ntypes = ntypes; sp.nx = nx; sp.ny = ny; sp.npairs = npairs;
+        sp.ff = formfactors; sp.out = f2(scratch);
+        // enough blocks to fill the machine a few times over, several slice pairs per block otherwise
+        const long long want_blocks = 8LL * rt::sm_count();
+        long long groups = (want_blocks + (long long)tiles * nf - 1) / ((long long)tiles * nf);
+        if (groups < 1) groups = 1;
+        if (groups > npairs) groups = npairs;
+        sp.pairs_per_block = (int)((npairs + groups - 1) / groups);
+        groups = (npairs + sp.pairs_per_block - 1) / sp.pairs_per_block;
+        int rc = go<StructureFactorPaired>(dim3(tiles, (unsigned)groups, nf), StructureFactorPaired::kSmem, s, sp, "structure_factor");
+        if (rc != PSB_OK) return rc;
+
+        PassParams p = base_params();
+        p.src = f2(scratch); p.dst = f2(scratch); p.src_img_stride = img; p.dst_img_stride = img;
+        cols_geometry(p, nx, ny);
+        rc = launch_line_pass(PASS_INV_COLS, p, nf * npairs, s);
+        if (rc != PSB_OK) return rc;
+        rows_geometry(p, nx, ny);
+        p.dst = f2(t_out) + f0 * nz * img;
+        p.scale = scale / ((float)nx * (float)ny);
+        p.sigma = sigma;
+        p.vout = v_out ? v_out + f0 * nz * img : nullptr;
+        p.pair_count = npairs; p.pair_nz = nz;
+        rc = launch_line_pass(PASS_RI2, p, nf * npairs, s);
+        if (rc != PSB_OK) return rc;
+    }
+    return PSB_OK;
 }
 
 int psb_transmission_from_potential(const float* v, psb_c64* t, long long n, float sigma, void* stream) {

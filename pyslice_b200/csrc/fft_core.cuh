@@ -146,7 +146,27 @@ struct SmemMap {
     static PSB_HD int at(int c, int q) { return COLS ? q * W + c : c * NP + q + (q >> 4); }
 };
 
-// One Stockham stage.  tw[k] = exp(-2*pi*i*k/N), k in [0, N).
+// elements per thread used for a given line size (host and device agree through this one rule)
+constexpr int elems_for(int N) { return N <= 128 ? 8 : 16; }
+
+// Twiddle table layout ("staged"): for every stage with NS > 1 a block of (R-1)*NS entries,
+//     block[(t-1)*NS + k] = exp(-2*pi*i*k*t/(NS*R)),  t = 1..R-1, k = 0..NS-1,
+// blocks concatenated in stage order.  Threads with consecutive k read consecutive entries, so the
+// loads coalesce (the flat exp(-2*pi*i*k/N) table made row-oriented passes fetch up to 15 cache
+// lines per warp request -- ncu profile r1 v1).
+template <int N, int E>
+constexpr int twiddle_offset(int stage) {
+    int off = 0, ns = 1;
+    for (int s = 0; s < stage; ++s) {
+        if (ns > 1) off += (Plan<N, E>::R[s] - 1) * ns;
+        ns *= Plan<N, E>::R[s];
+    }
+    return off;
+}
+template <int N, int E>
+constexpr int twiddle_count() { return twiddle_offset<N, E>(Plan<N, E>::S); }
+
+// One Stockham stage.  `tw` points at this stage's block of the staged twiddle table.
 template <int N, int E, int W, bool COLS, int R, int NS, int DIR, bool LAST, class Ctx>
 PSB_D void fft_stage(const Ctx& cx, float2 (&v)[E], float2* sm, int c, int j, const float2* PSB_RESTRICT tw) {
     constexpr int T = N / E;
@@ -160,10 +180,9 @@ PSB_D void fft_stage(const Ctx& cx, float2 (&v)[E], float2* sm, int c, int j, co
         const int b = j + m * T;
         if constexpr (NS > 1) {
             const int k = b & (NS - 1);
-            const int step = k * (N / (NS * R));
 #pragma unroll
             for (int t = 1; t < R; ++t) {
-                float2 w = __ldg(&tw[step * t]);
+                float2 w = __ldg(&tw[(t - 1) * NS + k]);
                 a[t] = DIR < 0 ? cmul(a[t], w) : cmulc(a[t], w);
             }
         }
@@ -191,14 +210,14 @@ PSB_D void fft_line(const Ctx& cx, float2 (&v)[E], float2* sm, int c, int j, con
     using P = Plan<N, E>;
     constexpr int R0 = P::R[0], R1 = P::R[1], R2 = P::R[2];
     fft_stage<N, E, W, COLS, R0, 1, DIR, P::S == 1>(cx, v, sm, c, j, tw);
-    if constexpr (P::S >= 2) fft_stage<N, E, W, COLS, R1, R0, DIR, P::S == 2>(cx, v, sm, c, j, tw);
-    if constexpr (P::S >= 3) fft_stage<N, E, W, COLS, R2, R0 * R1, DIR, P::S == 3>(cx, v, sm, c, j, tw);
-    if constexpr (P::S >= 4) fft_stage<N, E, W, COLS, P::R[3], R0 * R1 * R2, DIR, true>(cx, v, sm, c, j, tw);
+    if constexpr (P::S >= 2) fft_stage<N, E, W, COLS, R1, R0, DIR, P::S == 2>(cx, v, sm, c, j, tw + twiddle_offset<N, E>(1));
+    if constexpr (P::S >= 3) fft_stage<N, E, W, COLS, R2, R0 * R1, DIR, P::S == 3>(cx, v, sm, c, j, tw + twiddle_offset<N, E>(2));
+    if constexpr (P::S >= 4) fft_stage<N, E, W, COLS, P::R[3], R0 * R1 * R2, DIR, true>(cx, v, sm, c, j, tw + twiddle_offset<N, E>(3));
 }
 
 // Tables one line transform needs.  For the direct (power-of-two) path only `tw` is used.
 struct FftTables {
-    const float2* tw;      // [N]  exp(-2*pi*i*k/N)
+    const float2* tw;      // staged twiddle table of the (N, E) plan, see twiddle_offset
     const float2* chirp;   // [n]  exp(-i*pi*p^2/n)            (Bluestein only)
     const float2* bhat;    // [N]  FFT_N(wrapped conj chirp)/N  (Bluestein only)
     int n;                 // logical line length (== N on the direct path)

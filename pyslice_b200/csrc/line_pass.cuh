@@ -13,7 +13,8 @@
 //   C   cols  psi = IFFT_x(P * FFT_x(psi))                  second half of :292, :293, first half of :294
 //   CX  cols  out = fftshift(FFT_x(psi))                    calculators.py:286-287 (+ layout of :290,:186)
 //   CI  cols  S   = IFFT_x(S)                               potentials.py:336 (first half)
-//   RI  rows  t   = exp(i*sigma*Re(IFFT_y(S))*scale)        potentials.py:336-342 + multislice.py:281-282
+//   RI2 rows  t   = exp(i*sigma*Re(IFFT_y(S))*scale)        potentials.py:336-342 + multislice.py:281-282,
+//             two slices packed as Re/Im of one complex image (V is real)
 //   CP  cols  probe_k * ramp_x * ramp_y -> IFFT_x           multislice.py:221-226
 //   RP  rows  IFFT_y * 1/(nx*ny)                            multislice.py:226
 //   TW  cols  |fftshift FFT_t(psi - mean_t psi)|^2          tacaw_data.py:94-104
@@ -24,7 +25,7 @@ namespace psb {
 
 enum FftSel { F_NONE = 0, F_FWD = 1, F_INV = 2 };
 enum MidSel { M_NONE = 0, M_FULL = 1, M_SEP = 2 };
-enum StoreSel { S_PLAIN = 0, S_SHIFT = 1, S_TRANSMIT = 2, S_ABS2 = 3 };
+enum StoreSel { S_PLAIN = 0, S_SHIFT = 1, S_ABS2 = 3, S_TRANSMIT2 = 4 };
 
 struct PassParams {
     const float2* src;          // input images
@@ -45,15 +46,18 @@ struct PassParams {
     const float2* sep_p;
     const float2* sep_l;
     long long sep_img_stride_p, sep_img_stride_l;
-    float scale;                // S_PLAIN: output scale; S_TRANSMIT: V = Re(z)*scale
-    float sigma;                // S_TRANSMIT: t = exp(i*sigma*V)
-    float* vout;                // S_TRANSMIT: optional real potential output (same indexing as dst)
+    float scale;                // S_PLAIN: output scale; S_TRANSMIT2: V = Re/Im(z)*scale
+    float sigma;                // S_TRANSMIT2: t = exp(i*sigma*V)
+    float* vout;                // S_TRANSMIT2: optional real potential output (same indexing as dst)
     // S_SHIFT: dst index = (img % probes)*out_stride_probe + (img / probes)*out_stride_frame
     //                      + ((p + n/2) % n)*out_elem_stride + ((line + nlines/2) % nlines)*out_line_stride
     int probes;
     long long out_stride_probe, out_stride_frame, out_elem_stride, out_line_stride;
     // S_ABS2: real output fout[img*dst_img_stride + ((p + n/2) % n)*out_elem_stride + line*out_line_stride]
     float* fout;
+    // S_TRANSMIT2: image = frame*pair_count + m holds V_{2m} + i*V_{2m+1}; t of slice s of that frame goes to
+    //              dst[(frame*pair_nz + s)*dst_img_stride + ...] (and vout likewise)
+    int pair_count, pair_nz;
 };
 
 template <int N, int E, int W, bool COLS, bool BLUE, int F1, int MID, int F2, int ST, bool MEANSUB>
@@ -75,13 +79,20 @@ struct LinePass {
         const int n = p.line_len;
         float2* sm = reinterpret_cast<float2*>(cx.smem());
 
+        // n == N is a compile-time fact on the direct (power-of-two) path: no per-element bounds tests
+        auto in_line = [&](int q) { return BLUE ? q < n : true; };
+        const long long estep = (long long)T * p.elem_stride;     // pointer step between registers e, e+1
+
         const int simg = p.src_img_mod > 0 ? img % p.src_img_mod : img;
-        const float2* src = p.src + (long long)simg * p.src_img_stride + (long long)line * p.line_stride;
         float2 v[E];
+        {
+            const float2* src = p.src + (long long)simg * p.src_img_stride + (long long)line * p.line_stride
+                              + (long long)j * p.elem_stride;
 #pragma unroll
-        for (int e = 0; e < E; ++e) {
-            const int q = j + e * T;
-            v[e] = (line_ok && q < n) ? src[(long long)q * p.elem_stride] : make_float2(0.f, 0.f);
+            for (int e = 0; e < E; ++e) {
+                v[e] = (line_ok && in_line(j + e * T)) ? *src : make_float2(0.f, 0.f);
+                src += estep;
+            }
         }
 
         if constexpr (MEANSUB) {
@@ -100,28 +111,27 @@ struct LinePass {
             cx.sync();
 #pragma unroll
             for (int e = 0; e < E; ++e)
-                if (j + e * T < n) v[e] = csub(v[e], mean);
+                if (in_line(j + e * T)) v[e] = csub(v[e], mean);
         }
 
         if constexpr (F1 == F_FWD) dft_line<N, E, W, COLS, -1, BLUE>(cx, v, sm, c, j, p.tb);
         if constexpr (F1 == F_INV) dft_line<N, E, W, COLS, +1, BLUE>(cx, v, sm, c, j, p.tb);
 
         if constexpr (MID == M_FULL) {
-            const float2* mul = p.mul + (long long)(img / p.mul_img_div) * p.mul_img_stride + (long long)line * p.line_stride;
+            const float2* mul = p.mul + (long long)(img / p.mul_img_div) * p.mul_img_stride + (long long)line * p.line_stride
+                              + (long long)j * p.elem_stride;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int q = j + e * T;
-                if (line_ok && q < n) v[e] = cmul(v[e], __ldg(&mul[(long long)q * p.elem_stride]));
+                if (line_ok && in_line(j + e * T)) v[e] = cmul(v[e], __ldg(mul));
+                mul += estep;
             }
         }
         if constexpr (MID == M_SEP) {
             const float2 wl = line_ok ? __ldg(&p.sep_l[(long long)img * p.sep_img_stride_l + line]) : make_float2(0.f, 0.f);
-            const float2* sp = p.sep_p + (long long)img * p.sep_img_stride_p;
+            const float2* sp = p.sep_p + (long long)img * p.sep_img_stride_p + j;
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int q = j + e * T;
-                if (q < n) v[e] = cmul(v[e], cmul(__ldg(&sp[q]), wl));
-            }
+            for (int e = 0; e < E; ++e)
+                if (in_line(j + e * T)) v[e] = cmul(v[e], cmul(__ldg(&sp[e * T]), wl));
         }
 
         if constexpr (F2 == F_FWD) dft_line<N, E, W, COLS, -1, BLUE>(cx, v, sm, c, j, p.tb);
@@ -130,12 +140,13 @@ struct LinePass {
         if (!line_ok) return;   // after the last barrier
 
         if constexpr (ST == S_PLAIN) {
-            float2* dst = p.dst + (long long)img * p.dst_img_stride + (long long)line * p.line_stride;
+            float2* dst = p.dst + (long long)img * p.dst_img_stride + (long long)line * p.line_stride
+                        + (long long)j * p.elem_stride;
             const float sc = p.scale;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
-                const int q = j + e * T;
-                if (q < n) dst[(long long)q * p.elem_stride] = sc == 1.0f ? v[e] : cscale(v[e], sc);
+                if (in_line(j + e * T)) *dst = sc == 1.0f ? v[e] : cscale(v[e], sc);
+                dst += estep;
             }
         }
         if constexpr (ST == S_SHIFT) {
@@ -147,24 +158,32 @@ struct LinePass {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int q = j + e * T;
-                if (q < n) {
+                if (in_line(q)) {
                     int sq = q + half;
                     if (sq >= n) sq -= n;
                     dst[(long long)sq * p.out_elem_stride] = v[e];
                 }
             }
         }
-        if constexpr (ST == S_TRANSMIT) {
-            const long long base = (long long)img * p.dst_img_stride + (long long)line * p.line_stride;
+        if constexpr (ST == S_TRANSMIT2) {
+            const int fr = img / p.pair_count, m = img % p.pair_count;
+            const long long base0 = ((long long)fr * p.pair_nz + 2 * m) * p.dst_img_stride + (long long)line * p.line_stride;
+            const bool has_b = 2 * m + 1 < p.pair_nz;
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int q = j + e * T;
-                if (q < n) {
-                    const float V = v[e].x * p.scale;
+                if (in_line(q)) {
+                    const long long o = base0 + (long long)q * p.elem_stride;
+                    const float Va = v[e].x * p.scale, Vb = v[e].y * p.scale;
                     float sn, cs;
-                    sincosf(p.sigma * V, &sn, &cs);
-                    p.dst[base + (long long)q * p.elem_stride] = make_float2(cs, sn);
-                    if (p.vout) p.vout[base + (long long)q * p.elem_stride] = V;
+                    sincosf(p.sigma * Va, &sn, &cs);
+                    p.dst[o] = make_float2(cs, sn);
+                    if (p.vout) p.vout[o] = Va;
+                    if (has_b) {
+                        sincosf(p.sigma * Vb, &sn, &cs);
+                        p.dst[o + p.dst_img_stride] = make_float2(cs, sn);
+                        if (p.vout) p.vout[o + p.dst_img_stride] = Vb;
+                    }
                 }
             }
         }
@@ -174,7 +193,7 @@ struct LinePass {
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 const int q = j + e * T;
-                if (q < n) {
+                if (in_line(q)) {
                     int sq = q + half;
                     if (sq >= n) sq -= n;
                     dst[(long long)sq * p.out_elem_stride] = v[e].x * v[e].x + v[e].y * v[e].y;
@@ -192,11 +211,11 @@ enum PassKind {
     PASS_CX,       // cols:  FWD, shifted store
     PASS_INV_ROWS, // rows:  INV, plain (scaled)
     PASS_INV_COLS, // cols:  INV, plain (scaled)
-    PASS_RI,       // rows:  INV, transmission epilogue
     PASS_CP,       // cols:  sep multiply -> INV, plain
     PASS_FWD_ROWS, // rows:  FWD, plain
     PASS_FWD_COLS, // cols:  FWD, plain
     PASS_TW,       // cols:  mean-subtract -> FWD -> |.|^2 shifted
+    PASS_RI2,      // rows:  INV, paired transmission epilogue (two slices per complex image)
     PASS_KINDS
 };
 

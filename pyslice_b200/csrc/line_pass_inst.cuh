@@ -35,11 +35,11 @@ static int lp_kind(int kind, const PassParams& p, int n_img, cudaStream_t s) {
         case PASS_CX:       return lp_go<true, BLUE, F_NONE, M_NONE, F_FWD, S_SHIFT, false>(p, n_img, s);
         case PASS_INV_ROWS: return lp_go<false, BLUE, F_NONE, M_NONE, F_INV, S_PLAIN, false>(p, n_img, s);
         case PASS_INV_COLS: return lp_go<true, BLUE, F_NONE, M_NONE, F_INV, S_PLAIN, false>(p, n_img, s);
-        case PASS_RI:       return lp_go<false, BLUE, F_NONE, M_NONE, F_INV, S_TRANSMIT, false>(p, n_img, s);
         case PASS_CP:       return lp_go<true, BLUE, F_NONE, M_SEP, F_INV, S_PLAIN, false>(p, n_img, s);
         case PASS_FWD_ROWS: return lp_go<false, BLUE, F_NONE, M_NONE, F_FWD, S_PLAIN, false>(p, n_img, s);
         case PASS_FWD_COLS: return lp_go<true, BLUE, F_NONE, M_NONE, F_FWD, S_PLAIN, false>(p, n_img, s);
         case PASS_TW:       return lp_go<true, BLUE, F_NONE, M_NONE, F_FWD, S_ABS2, true>(p, n_img, s);
+        case PASS_RI2:      return lp_go<false, BLUE, F_NONE, M_NONE, F_INV, S_TRANSMIT2, false>(p, n_img, s);
     }
     return fail(PSB_ERR_INVALID, "unknown pass kind");
 }

@@ -130,15 +130,6 @@ struct BinCompact {
     }
 };
 
-struct SfParams {
-    const int* offsets;         // (F, nseg+1)
-    const unsigned int* ux;     // (F, cap)
-    const unsigned int* uy;
-    int cap, nz, ntypes, nx, ny;
-    const float* ff;            // (ntypes, nx, ny) form factors on the k grid (fftfreq order)
-    float2* out;                // (F, nz, nx, ny) structure factor x form factor
-};
-
 // exp(-2*pi*i*m*u) with u a 32-bit fraction: the integer product wraps modulo one turn exactly
 PSB_D float2 unit_phase(int m, unsigned int u) {
     const int ph = (int)((unsigned int)m * u);                 // signed turn fraction * 2^32
@@ -147,94 +138,147 @@ PSB_D float2 unit_phase(int m, unsigned int u) {
     return make_float2(c, -s);
 }
 
-// One CTA per 64x64 tile of (kx, ky), slice and frame; 256 threads x (4 x 4) outputs.
-struct StructureFactor {
+// ---- Hermitian, slice-paired structure factor ---------------------------------------------------
+// V_s is real, so (i) only the half spectrum ky in [0, ny/2] is summed and the other half is written
+// as its conjugate mirror, and (ii) two slices share one complex inverse FFT:
+//     Z_m = S'_{2m} + i*S'_{2m+1}   ->   IFFT2(Z_m) = V_{2m} + i*V_{2m+1}.
+// S' is the Hermitian part of the reference's spectrum: its Re(ifft2(S)) (potentials.py:336-337)
+// discards the anti-Hermitian part, which is non-zero only on the self-conjugate Nyquist lines of an
+// even-sized grid.  There e^{-2 pi i k x} is replaced by its real part (exactly the Hermitian part of
+// the line); at the (Nyquist, Nyquist) corner the product's real part needs the extra -sin*sin term.
+struct SfPairParams {
+    const int* offsets;         // (F, nseg+1)
+    const unsigned int* ux;     // (F, cap)
+    const unsigned int* uy;
+    int cap, nz, ntypes, nx, ny, npairs, pairs_per_block;
+    const float* ff;            // (ntypes, nx, ny)
+    float2* out;                // (F, npairs, nx, ny)
+};
+
+struct StructureFactorPaired {
     static constexpr int kThreads = 256;
     static constexpr int kMinBlocks = 2;
-    static constexpr int TILE = 64;
-    static constexpr int CH = 32;      // atoms staged per chunk
-    static constexpr size_t kSmem = 2 * CH * TILE * sizeof(float2);
+    static constexpr int TX = 64, TY = 32;   // kx x ky tile; thread: 4 kx (stride 16) x 2 ky (stride 16)
+    static constexpr int CH = 32;
+    static constexpr size_t kSmem = CH * (TX + TY) * sizeof(float2) + 2 * CH * sizeof(float);
+
     template <class Ctx>
-    static PSB_D void run(const Ctx& cx, const SfParams& p) {
-        const int tiles_y = (p.ny + TILE - 1) / TILE;
-        const int kx0 = (cx.bx() / tiles_y) * TILE, ky0 = (cx.bx() % tiles_y) * TILE;
-        const int s = cx.by(), f = cx.bz();
+    static PSB_D void run(const Ctx& cx, const SfPairParams& p) {
+        const int nyh = p.ny / 2 + 1;
+        const int tiles_y = (nyh + TY - 1) / TY;
+        const int kx0 = (cx.bx() / tiles_y) * TX, ky0 = (cx.bx() % tiles_y) * TY;
+        const int f = cx.bz();
         const int tid = cx.tid(), tx = tid % 16, ty = tid / 16;
-        float2* ex = reinterpret_cast<float2*>(cx.smem());    // [CH][TILE]
-        float2* ey = ex + CH * TILE;
+        float2* ex = reinterpret_cast<float2*>(cx.smem());     // [CH][TX]
+        float2* ey = ex + CH * TX;                              // [CH][TY]
+        float* snx = reinterpret_cast<float*>(ey + CH * TY);    // sin part of ex at the x Nyquist index
+        float* sny = snx + CH;
         const int nseg = p.nz * p.ntypes;
         const int* off = p.offsets + (long long)f * (nseg + 1);
         const unsigned int* ux = p.ux + (long long)f * p.cap;
         const unsigned int* uy = p.uy + (long long)f * p.cap;
-        const int hx = (p.nx + 1) / 2, hy = (p.ny + 1) / 2;   // fftfreq: index i -> i (i < h) or i-n
+        const int hx = (p.nx + 1) / 2, hy = (p.ny + 1) / 2;
+        const int nyq_x = (p.nx % 2 == 0) ? p.nx / 2 : -1;
+        const int nyq_y = (p.ny % 2 == 0) ? p.ny / 2 : -1;
+        const bool corner_tile = nyq_x >= kx0 && nyq_x < kx0 + TX && nyq_y >= ky0 && nyq_y < ky0 + TY;
 
-        float2 tot[4][4];
+        int kxs[4], kys[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i) kxs[i] = kx0 + ty + 16 * i;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) tot[i][k] = make_float2(0.f, 0.f);
+        for (int k = 0; k < 2; ++k) kys[k] = ky0 + tx + 16 * k;
 
-        for (int t = 0; t < p.ntypes; ++t) {
-            const int b = off[s * p.ntypes + t], e = off[s * p.ntypes + t + 1];
-            if (b == e) continue;                              // block-uniform
-            float2 acc[4][4];
+        const int m0 = cx.by() * p.pairs_per_block;
+        const int m1 = m0 + p.pairs_per_block < p.npairs ? m0 + p.pairs_per_block : p.npairs;
+        for (int m = m0; m < m1; ++m) {
+            float2 tot[2][4][2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int h = 0; h < 2; ++h)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) acc[i][k] = make_float2(0.f, 0.f);
-            for (int c0 = b; c0 < e; c0 += CH) {
-                const int nc = e - c0 < CH ? e - c0 : CH;
-                cx.sync();
-                for (int w = tid; w < nc * 2 * TILE; w += kThreads) {
-                    const int a = w / (2 * TILE), r = w % (2 * TILE);
-                    if (r < TILE) {
-                        const int i = kx0 + r;
-                        ex[a * TILE + r] = unit_phase(i < hx ? i : i - p.nx, ux[c0 + a]);
-                    } else {
-                        const int i = ky0 + r - TILE;
-                        ey[a * TILE + r - TILE] = unit_phase(i < hy ? i : i - p.ny, uy[c0 + a]);
-                    }
-                }
-                cx.sync();
-                for (int a = 0; a < nc; ++a) {
-                    float2 xs[4], ys[4];
+                for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) xs[i] = ex[a * TILE + ty + 16 * i];
+                    for (int k = 0; k < 2; ++k) tot[h][i][k] = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) ys[k] = ey[a * TILE + tx + 16 * k];
+            for (int h = 0; h < 2; ++h) {
+                const int s = 2 * m + h;
+                if (s >= p.nz) continue;                          // block-uniform
+                for (int t = 0; t < p.ntypes; ++t) {
+                    const int b = off[s * p.ntypes + t], e = off[s * p.ntypes + t + 1];
+                    if (b == e) continue;                          // block-uniform
+                    float2 acc[4][2];
+                    float corr = 0.f;
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            acc[i][k].x += xs[i].x * ys[k].x - xs[i].y * ys[k].y;
-                            acc[i][k].y += xs[i].x * ys[k].y + xs[i].y * ys[k].x;
+                        for (int k = 0; k < 2; ++k) acc[i][k] = make_float2(0.f, 0.f);
+                    for (int c0 = b; c0 < e; c0 += CH) {
+                        const int nc = e - c0 < CH ? e - c0 : CH;
+                        cx.sync();
+                        for (int w = tid; w < nc * (TX + TY); w += kThreads) {
+                            const int a = w / (TX + TY), r = w % (TX + TY);
+                            if (r < TX) {
+                                const int i = kx0 + r;
+                                float2 z = unit_phase(i < hx ? i : i - p.nx, ux[c0 + a]);
+                                if (i == nyq_x) { snx[a] = z.y; z.y = 0.f; }
+                                ex[a * TX + r] = z;
+                            } else {
+                                const int i = ky0 + r - TX;
+                                float2 z = unit_phase(i < hy ? i : i - p.ny, uy[c0 + a]);
+                                if (i == nyq_y) { sny[a] = z.y; z.y = 0.f; }
+                                ey[a * TY + r - TX] = z;
+                            }
+                        }
+                        cx.sync();
+                        for (int a = 0; a < nc; ++a) {
+                            float2 xs[4], ys[2];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) xs[i] = ex[a * TX + ty + 16 * i];
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) ys[k] = ey[a * TY + tx + 16 * k];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) {
+                                    acc[i][k].x += xs[i].x * ys[k].x - xs[i].y * ys[k].y;
+                                    acc[i][k].y += xs[i].x * ys[k].y + xs[i].y * ys[k].x;
+                                }
+                        }
+                        if (corner_tile) {                         // block-uniform: Re(ex*ey) = cos*cos - sin*sin
+                            for (int a = 0; a < nc; ++a) corr += snx[a] * sny[a];
+                        }
+                    }
+                    const float* ff = p.ff + (long long)t * p.nx * p.ny;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            if (kxs[i] < p.nx && kys[k] < nyh) {
+                                const float w = __ldg(&ff[(long long)kxs[i] * p.ny + kys[k]]);
+                                float re = acc[i][k].x;
+                                if (kxs[i] == nyq_x && kys[k] == nyq_y) re -= corr;
+                                tot[h][i][k].x += re * w;
+                                tot[h][i][k].y += acc[i][k].y * w;
+                            }
                         }
                 }
             }
-            const float* ff = p.ff + (long long)t * p.nx * p.ny;
+            // Z[k] = A + iB,  Z[-k] = conj(A) + i*conj(B)
+            float2* out = p.out + ((long long)f * p.npairs + m) * p.nx * p.ny;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int kx = kx0 + ty + 16 * i;
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const int ky = ky0 + tx + 16 * k;
-                    if (kx < p.nx && ky < p.ny) {
-                        const float w = __ldg(&ff[(long long)kx * p.ny + ky]);
-                        tot[i][k].x += acc[i][k].x * w;
-                        tot[i][k].y += acc[i][k].y * w;
+                for (int k = 0; k < 2; ++k) {
+                    const int kx = kxs[i], ky = kys[k];
+                    if (kx < p.nx && ky < nyh) {
+                        const float2 A = tot[0][i][k], B = tot[1][i][k];
+                        out[(long long)kx * p.ny + ky] = make_float2(A.x - B.y, A.y + B.x);
+                        const int my = ky == 0 ? 0 : p.ny - ky;
+                        if (my >= nyh) {
+                            const int mx = kx == 0 ? 0 : p.nx - kx;
+                            out[(long long)mx * p.ny + my] = make_float2(A.x + B.y, B.x - A.y);
+                        }
                     }
                 }
-            }
-        }
-        float2* out = p.out + ((long long)f * p.nz + s) * p.nx * p.ny;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int kx = kx0 + ty + 16 * i;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int ky = ky0 + tx + 16 * k;
-                if (kx < p.nx && ky < p.ny) out[(long long)kx * p.ny + ky] = tot[i][k];
-            }
         }
     }
 };

@@ -50,6 +50,39 @@ void host_fft(std::vector<cd>& a) {   // in-place radix-2, forward, power-of-two
     }
 }
 
+// staged twiddle table of the plan used for line size N (layout: fft_core.cuh, twiddle_offset)
+template <int N>
+std::vector<cd> staged_for() {
+    constexpr int E = elems_for(N);
+    using P = Plan<N, E>;
+    std::vector<cd> out;
+    int ns = 1;
+    for (int s = 0; s < P::S; ++s) {
+        const int R = P::R[s];
+        if (ns > 1)
+            for (int t = 1; t < R; ++t)
+                for (int k = 0; k < ns; ++k) out.push_back(unit((long long)k * t, (long long)ns * R, -1));
+        ns *= R;
+    }
+    if (out.empty()) out.push_back(cd(1, 0));
+    return out;
+}
+std::vector<cd> staged_twiddles(int N) {
+    switch (N) {
+        case 16: return staged_for<16>();
+        case 32: return staged_for<32>();
+        case 64: return staged_for<64>();
+        case 128: return staged_for<128>();
+        case 256: return staged_for<256>();
+        case 512: return staged_for<512>();
+        case 1024: return staged_for<1024>();
+        case 2048: return staged_for<2048>();
+        case 4096: return staged_for<4096>();
+        case 8192: return staged_for<8192>();
+    }
+    return std::vector<cd>(1, cd(1, 0));
+}
+
 float2* upload(const std::vector<cd>& h, cudaStream_t s) {
     std::vector<float2> f(h.size());
     for (size_t i = 0; i < h.size(); ++i) f[i] = make_float2((float)h[i].real(), (float)h[i].imag());
@@ -89,8 +122,7 @@ int get_fft_tables(int n, FftTables* out, int* N_out, bool* blue_out, cudaStream
         auto tk = std::make_pair(dev, N);
         auto tt = g_tw.find(tk);
         if (tt == g_tw.end()) {
-            std::vector<cd> tw(N);
-            for (int k = 0; k < N; ++k) tw[k] = unit(k, N, -1);
+            std::vector<cd> tw = staged_twiddles(N);
             float2* d = upload(tw, s);
             if (!d) return PSB_ERR_NOMEM;
             tt = g_tw.emplace(tk, d).first;

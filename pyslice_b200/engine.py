@@ -19,6 +19,8 @@ from . import _lib, hostmath
 PSI_BATCH_BYTES = 48 << 20
 # Upper bound for the transmission-function buffer of one frame batch.
 T_BATCH_BYTES = 24 << 30
+# Workspace of the potential build (slice-paired spectra); frames are chunked to fit it.
+SCRATCH_BYTES = 2 << 30
 
 
 class PhaseTimer:
@@ -187,7 +189,7 @@ def bin_atoms(plan: SlicePlan, positions: torch.Tensor):
 
 
 def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential: bool = False,
-                       out: Optional[torch.Tensor] = None):
+                       out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None):
     """positions (F, A, 3) float64 on device -> t (F, nz, nx, ny) complex64 [, V float32]."""
     F, A, _ = positions.shape
     dev = plan.device
@@ -195,10 +197,15 @@ def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential:
     t = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device=dev)
     V = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev) if want_potential else None
     scale = 1.0 / (plan.dx ** 2 * plan.dy ** 2)
+    per_frame = ((plan.nz + 1) // 2) * plan.nx * plan.ny
+    n_scratch = per_frame * max(1, min(F, SCRATCH_BYTES // (8 * per_frame)))
+    if scratch is None or scratch.numel() < n_scratch:
+        scratch = torch.empty((n_scratch,), dtype=torch.complex64, device=dev)
     L = _lib.lib()
     _lib.check(L.psb_build_transmission(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
                                         plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
-                                        t.data_ptr(), V.data_ptr() if V is not None else None, _stream(dev)),
+                                        t.data_ptr(), V.data_ptr() if V is not None else None, scratch.data_ptr(),
+                                        scratch.numel(), _stream(dev)),
                "psb_build_transmission")
     return (t, V) if want_potential else t
 
