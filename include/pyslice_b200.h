@@ -59,8 +59,8 @@ int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames
  * formfactors (ntypes, nx, ny) float32 = Kirkland f_e on the fftfreq grid (host table, potentials.py:86-96).
  * t_out (F, nz, nx, ny) complex64 = exp(i*sigma*V), V = Re IFFT2(S) * scale  with scale = 1/(dx^2 dy^2)
  * (the 1/(nx*ny) of the inverse FFT is applied internally).  v_out (same shape, float32) optional.
- * scratch: complex64 workspace of scratch_elems >= ((nz+1)/2)*nx*ny elements (one frame); frames are
- * processed in chunks that fit it.  V is real, so two slices share one complex inverse FFT and only
+ * scratch: complex64 workspace of scratch_elems >= nx*ny elements; the stack is built in chunks of
+ * slice-pair images that fit it (size it to stay L2-resident, e.g. 32 MiB).  V is real, so two slices share one complex inverse FFT and only
  * half of each spectrum is summed (the Hermitian part -- exactly what the reference's Re() keeps). */
 int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
                            int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,

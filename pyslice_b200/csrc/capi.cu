@@ -100,43 +100,57 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
     cudaStream_t s = as_stream(stream);
     const long long img = (long long)nx * ny;
     const int npairs = (nz + 1) / 2;
-    if (npairs > 65535) return fail(PSB_ERR_UNSUPPORTED, "psb_build_transmission: too many slices");
-    long long chunk = scratch_elems / (npairs * img);          // frames per chunk that fit the scratch
-    if (chunk < 1) return fail(PSB_ERR_INVALID, "psb_build_transmission: scratch smaller than one frame ((nz+1)/2*nx*ny elements)");
-    if (chunk > 65535 / npairs) chunk = 65535 / npairs;         // grid.y limit of the line passes
-    if (chunk < 1) chunk = 1;
+    // Work in chunks of slice-pair images small enough to stay in L2 between the three kernels
+    // (structure factor -> column IFFT -> row IFFT + transmission), so only t itself goes to HBM.
+    long long chunk_imgs = scratch_elems / img;
+    if (chunk_imgs < 1) return fail(PSB_ERR_INVALID, "psb_build_transmission: scratch smaller than one image (nx*ny elements)");
+    if (chunk_imgs > 65535) chunk_imgs = 65535;
+    int mc, fc;                                                  // pairs per chunk, frames per chunk
+    if (chunk_imgs >= npairs) {
+        mc = npairs;
+        fc = (int)(chunk_imgs / npairs);
+        if (fc > n_frames) fc = n_frames;
+    } else {
+        mc = (int)chunk_imgs;
+        fc = 1;
+    }
     const int nseg = nz * ntypes;
     const int TXs = StructureFactorPaired::TX, TYs = StructureFactorPaired::TY;
-    const int tiles = ((nx + TXs - 1) / TXs) * ((ny / 2 + 1 + TYs - 1) / TYs);
-    for (long long f0 = 0; f0 < n_frames; f0 += chunk) {
-        const int nf = (int)(n_frames - f0 < chunk ? n_frames - f0 : chunk);
-        SfPairParams sp;
-        sp.offsets = offsets + f0 * (nseg + 1); sp.ux = ux + f0 * 2 * n_atoms; sp.uy = uy + f0 * 2 * n_atoms;
-        sp.cap = 2 * n_atoms; sp.nz = nz; sp.ntypes = ntypes; sp.nx = nx; sp.ny = ny; sp.npairs = npairs;
-        sp.ff = formfactors; sp.out = f2(scratch);
-        // enough blocks to fill the machine a few times over, several slice pairs per block otherwise
-        const long long want_blocks = 8LL * rt::sm_count();
-        long long groups = (want_blocks + (long long)tiles * nf - 1) / ((long long)tiles * nf);
-        if (groups < 1) groups = 1;
-        if (groups > npairs) groups = npairs;
-        sp.pairs_per_block = (int)((npairs + groups - 1) / groups);
-        groups = (npairs + sp.pairs_per_block - 1) / sp.pairs_per_block;
-        int rc = go<StructureFactorPaired>(dim3(tiles, (unsigned)groups, nf), StructureFactorPaired::kSmem, s, sp, "structure_factor");
-        if (rc != PSB_OK) return rc;
+    const int tiles = ((StructureFactorPaired::slots(nx) + TXs - 1) / TXs) * ((StructureFactorPaired::slots(ny) + TYs - 1) / TYs);
+    for (int f0 = 0; f0 < n_frames; f0 += fc) {
+        const int nf = n_frames - f0 < fc ? n_frames - f0 : fc;
+        for (int mb = 0; mb < npairs; mb += mc) {
+            const int nm = npairs - mb < mc ? npairs - mb : mc;
+            SfPairParams sp;
+            sp.offsets = offsets + (long long)f0 * (nseg + 1);
+            sp.ux = ux + (long long)f0 * 2 * n_atoms; sp.uy = uy + (long long)f0 * 2 * n_atoms;
+            sp.cap = 2 * n_atoms; sp.nz = nz; sp.ntypes = ntypes; sp.nx = nx; sp.ny = ny;
+            sp.pair_begin = mb; sp.pair_count = nm;
+            sp.ff = formfactors; sp.out = f2(scratch);
+            // several pairs per block only when one pair per block would already overfill the machine
+            const long long want_blocks = 8LL * rt::sm_count();
+            long long groups = (want_blocks + (long long)tiles * nf - 1) / ((long long)tiles * nf);
+            if (groups < 1) groups = 1;
+            if (groups > nm) groups = nm;
+            sp.pairs_per_block = (int)((nm + groups - 1) / groups);
+            groups = (nm + sp.pairs_per_block - 1) / sp.pairs_per_block;
+            int rc = go<StructureFactorPaired>(dim3(tiles, (unsigned)groups, nf), StructureFactorPaired::kSmem, s, sp, "structure_factor");
+            if (rc != PSB_OK) return rc;
 
-        PassParams p = base_params();
-        p.src = f2(scratch); p.dst = f2(scratch); p.src_img_stride = img; p.dst_img_stride = img;
-        cols_geometry(p, nx, ny);
-        rc = launch_line_pass(PASS_INV_COLS, p, nf * npairs, s);
-        if (rc != PSB_OK) return rc;
-        rows_geometry(p, nx, ny);
-        p.dst = f2(t_out) + f0 * nz * img;
-        p.scale = scale / ((float)nx * (float)ny);
-        p.sigma = sigma;
-        p.vout = v_out ? v_out + f0 * nz * img : nullptr;
-        p.pair_count = npairs; p.pair_nz = nz;
-        rc = launch_line_pass(PASS_RI2, p, nf * npairs, s);
-        if (rc != PSB_OK) return rc;
+            PassParams p = base_params();
+            p.src = f2(scratch); p.dst = f2(scratch); p.src_img_stride = img; p.dst_img_stride = img;
+            cols_geometry(p, nx, ny);
+            rc = launch_line_pass(PASS_INV_COLS, p, nf * nm, s);
+            if (rc != PSB_OK) return rc;
+            rows_geometry(p, nx, ny);
+            p.dst = f2(t_out) + (long long)f0 * nz * img;
+            p.scale = scale / ((float)nx * (float)ny);
+            p.sigma = sigma;
+            p.vout = v_out ? v_out + (long long)f0 * nz * img : nullptr;
+            p.pair_count = nm; p.pair_nz = nz; p.pair_begin = mb;
+            rc = launch_line_pass(PASS_RI2, p, nf * nm, s);
+            if (rc != PSB_OK) return rc;
+        }
     }
     return PSB_OK;
 }

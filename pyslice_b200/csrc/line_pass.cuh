@@ -55,9 +55,9 @@ struct PassParams {
     long long out_stride_probe, out_stride_frame, out_elem_stride, out_line_stride;
     // S_ABS2: real output fout[img*dst_img_stride + ((p + n/2) % n)*out_elem_stride + line*out_line_stride]
     float* fout;
-    // S_TRANSMIT2: image = frame*pair_count + m holds V_{2m} + i*V_{2m+1}; t of slice s of that frame goes to
-    //              dst[(frame*pair_nz + s)*dst_img_stride + ...] (and vout likewise)
-    int pair_count, pair_nz;
+    // S_TRANSMIT2: image = frame*pair_count + ml holds V_{2m} + i*V_{2m+1} with m = pair_begin + ml; t of slice s
+    //              of that frame goes to dst[(frame*pair_nz + s)*dst_img_stride + ...] (and vout likewise)
+    int pair_count, pair_nz, pair_begin;
 };
 
 template <int N, int E, int W, bool COLS, bool BLUE, int F1, int MID, int F2, int ST, bool MEANSUB>
@@ -166,7 +166,7 @@ struct LinePass {
             }
         }
         if constexpr (ST == S_TRANSMIT2) {
-            const int fr = img / p.pair_count, m = img % p.pair_count;
+            const int fr = img / p.pair_count, m = p.pair_begin + img % p.pair_count;
             const long long base0 = ((long long)fr * p.pair_nz + 2 * m) * p.dst_img_stride + (long long)line * p.line_stride;
             const bool has_b = 2 * m + 1 < p.pair_nz;
 #pragma unroll

@@ -138,145 +138,210 @@ PSB_D float2 unit_phase(int m, unsigned int u) {
     return make_float2(c, -s);
 }
 
-// ---- Hermitian, slice-paired structure factor ---------------------------------------------------
-// V_s is real, so (i) only the half spectrum ky in [0, ny/2] is summed and the other half is written
-// as its conjugate mirror, and (ii) two slices share one complex inverse FFT:
-//     Z_m = S'_{2m} + i*S'_{2m+1}   ->   IFFT2(Z_m) = V_{2m} + i*V_{2m+1}.
-// S' is the Hermitian part of the reference's spectrum: its Re(ifft2(S)) (potentials.py:336-337)
-// discards the anti-Hermitian part, which is non-zero only on the self-conjugate Nyquist lines of an
-// even-sized grid.  There e^{-2 pi i k x} is replaced by its real part (exactly the Hermitian part of
-// the line); at the (Nyquist, Nyquist) corner the product's real part needs the extra -sin*sin term.
+// ---- quarter-spectrum, slice-paired structure factor ----------------------------------------------
+// V_s is real and e^{-2 pi i k x} = c - i*s with c even / s odd in k, so with the four real sums
+//     CC = sum cx*cy,  SS = sum sx*sy,  CS = sum cx*sy,  SC = sum sx*cy      (4 FMA per atom and slot)
+// over the atoms of a (slice, type), one slot (kx, ky) with kx, ky >= 0 yields all four spectrum entries
+//     S[+kx,+ky] = (CC-SS) - i(CS+SC)        S[-kx,+ky] = (CC+SS) - i(CS-SC)
+//     S[+kx,-ky] = conj S[-kx,+ky]           S[-kx,-ky] = conj S[+kx,+ky]
+// i.e. one real FMA per complex spectrum entry instead of four.  Two slices then share one complex
+// inverse FFT: Z_m = S'_{2m} + i*S'_{2m+1}  ->  IFFT2(Z_m) = V_{2m} + i*V_{2m+1}.
+//
+// S' is the Hermitian part of the reference's spectrum: its Re(ifft2(S)) (potentials.py:336-337) drops the
+// anti-Hermitian part, which is non-zero only on the self-conjugate Nyquist lines of an even-sized axis,
+// where the Hermitian part of e^{-2 pi i k x} is its cosine.  The zero-frequency slot has s = 0, so the
+// Nyquist cosine rides in that unused component: slot 0 stores (1, cos(pi*n*u)) and its SC / SS sums are
+// the Nyquist line's CC / CS.  Only the (Nyquist, Nyquist) corner needs one extra term, -sum sin*sin.
 struct SfPairParams {
     const int* offsets;         // (F, nseg+1)
     const unsigned int* ux;     // (F, cap)
     const unsigned int* uy;
-    int cap, nz, ntypes, nx, ny, npairs, pairs_per_block;
+    int cap, nz, ntypes, nx, ny;
+    int pair_begin, pair_count; // this launch covers slice pairs [pair_begin, pair_begin + pair_count) of every frame
+    int pairs_per_block;
     const float* ff;            // (ntypes, nx, ny)
-    float2* out;                // (F, npairs, nx, ny)
+    float2* out;                // (F, pair_count, nx, ny)
 };
 
 struct StructureFactorPaired {
     static constexpr int kThreads = 256;
     static constexpr int kMinBlocks = 2;
-    static constexpr int TX = 64, TY = 32;   // kx x ky tile; thread: 4 kx (stride 16) x 2 ky (stride 16)
-    static constexpr int CH = 32;
-    static constexpr size_t kSmem = CH * (TX + TY) * sizeof(float2) + 2 * CH * sizeof(float);
+    static constexpr int TX = 64, TY = 32;   // slots per tile; thread: 4 kx slots (stride 16) x 2 ky slots (stride 16)
+    static constexpr int CH = 32;            // atoms staged per chunk
+    static constexpr size_t kSmem = CH * (TX + TY) * sizeof(float2) + 2 * CH * sizeof(float) + 32 * kThreads * sizeof(float);
+
+    // number of non-negative-frequency slots of an axis (the Nyquist line of an even axis rides in slot 0)
+    static PSB_HD int slots(int n) { return (n % 2 == 0) ? n / 2 : (n + 1) / 2; }
 
     template <class Ctx>
     static PSB_D void run(const Ctx& cx, const SfPairParams& p) {
-        const int nyh = p.ny / 2 + 1;
-        const int tiles_y = (nyh + TY - 1) / TY;
+        const int nsx = slots(p.nx), nsy = slots(p.ny);
+        const int tiles_y = (nsy + TY - 1) / TY;
         const int kx0 = (cx.bx() / tiles_y) * TX, ky0 = (cx.bx() % tiles_y) * TY;
         const int f = cx.bz();
         const int tid = cx.tid(), tx = tid % 16, ty = tid / 16;
-        float2* ex = reinterpret_cast<float2*>(cx.smem());     // [CH][TX]
-        float2* ey = ex + CH * TX;                              // [CH][TY]
-        float* snx = reinterpret_cast<float*>(ey + CH * TY);    // sin part of ex at the x Nyquist index
+        float2* ex = reinterpret_cast<float2*>(cx.smem());     // [CH][TX]  (cx, sx)
+        float2* ey = ex + CH * TX;                              // [CH][TY]  (cy, sy)
+        float* snx = reinterpret_cast<float*>(ey + CH * TY);    // sin(pi*nx*u) per staged atom (corner term)
         float* sny = snx + CH;
+        float* stash = sny + CH;                                // [32][kThreads] totals of the pair's first slice
         const int nseg = p.nz * p.ntypes;
         const int* off = p.offsets + (long long)f * (nseg + 1);
         const unsigned int* ux = p.ux + (long long)f * p.cap;
         const unsigned int* uy = p.uy + (long long)f * p.cap;
-        const int hx = (p.nx + 1) / 2, hy = (p.ny + 1) / 2;
-        const int nyq_x = (p.nx % 2 == 0) ? p.nx / 2 : -1;
-        const int nyq_y = (p.ny % 2 == 0) ? p.ny / 2 : -1;
-        const bool corner_tile = nyq_x >= kx0 && nyq_x < kx0 + TX && nyq_y >= ky0 && nyq_y < ky0 + TY;
+        const bool nq_x = p.nx % 2 == 0, nq_y = p.ny % 2 == 0;
+        const bool corner_tile = kx0 == 0 && ky0 == 0 && nq_x && nq_y;
 
-        int kxs[4], kys[2];
+        int gx[4], gy[2];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) kxs[i] = kx0 + ty + 16 * i;
+        for (int i = 0; i < 4; ++i) gx[i] = kx0 + ty + 16 * i;
 #pragma unroll
-        for (int k = 0; k < 2; ++k) kys[k] = ky0 + tx + 16 * k;
+        for (int k = 0; k < 2; ++k) gy[k] = ky0 + tx + 16 * k;
 
-        const int m0 = cx.by() * p.pairs_per_block;
-        const int m1 = m0 + p.pairs_per_block < p.npairs ? m0 + p.pairs_per_block : p.npairs;
-        for (int m = m0; m < m1; ++m) {
-            float2 tot[2][4][2];
+        const int l0 = cx.by() * p.pairs_per_block;
+        const int l1 = l0 + p.pairs_per_block < p.pair_count ? l0 + p.pairs_per_block : p.pair_count;
+        for (int ml = l0; ml < l1; ++ml) {
+            const int m = p.pair_begin + ml;
+            float tot[4][2][4];     // [i][k][cc, ss, cs, sc], already multiplied by the form factor
 #pragma unroll
-            for (int h = 0; h < 2; ++h)
+            for (int h = 0; h < 2; ++h) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int k = 0; k < 2; ++k) tot[h][i][k] = make_float2(0.f, 0.f);
+                    for (int k = 0; k < 2; ++k)
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
+                        for (int q = 0; q < 4; ++q) tot[i][k][q] = 0.f;
                 const int s = 2 * m + h;
-                if (s >= p.nz) continue;                          // block-uniform
-                for (int t = 0; t < p.ntypes; ++t) {
-                    const int b = off[s * p.ntypes + t], e = off[s * p.ntypes + t + 1];
-                    if (b == e) continue;                          // block-uniform
-                    float2 acc[4][2];
-                    float corr = 0.f;
+                if (s < p.nz) {                                   // block-uniform
+                    for (int t = 0; t < p.ntypes; ++t) {
+                        const int b = off[s * p.ntypes + t], e = off[s * p.ntypes + t + 1];
+                        if (b == e) continue;                      // block-uniform
+                        float acc[4][2][4];
+                        float corr = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                        for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) acc[i][k] = make_float2(0.f, 0.f);
-                    for (int c0 = b; c0 < e; c0 += CH) {
-                        const int nc = e - c0 < CH ? e - c0 : CH;
-                        cx.sync();
-                        for (int w = tid; w < nc * (TX + TY); w += kThreads) {
-                            const int a = w / (TX + TY), r = w % (TX + TY);
-                            if (r < TX) {
-                                const int i = kx0 + r;
-                                float2 z = unit_phase(i < hx ? i : i - p.nx, ux[c0 + a]);
-                                if (i == nyq_x) { snx[a] = z.y; z.y = 0.f; }
-                                ex[a * TX + r] = z;
-                            } else {
-                                const int i = ky0 + r - TX;
-                                float2 z = unit_phase(i < hy ? i : i - p.ny, uy[c0 + a]);
-                                if (i == nyq_y) { sny[a] = z.y; z.y = 0.f; }
-                                ey[a * TY + r - TX] = z;
-                            }
-                        }
-                        cx.sync();
-                        for (int a = 0; a < nc; ++a) {
-                            float2 xs[4], ys[2];
+                            for (int k = 0; k < 2; ++k)
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) xs[i] = ex[a * TX + ty + 16 * i];
-#pragma unroll
-                            for (int k = 0; k < 2; ++k) ys[k] = ey[a * TY + tx + 16 * k];
-#pragma unroll
-                            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                                for (int k = 0; k < 2; ++k) {
-                                    acc[i][k].x += xs[i].x * ys[k].x - xs[i].y * ys[k].y;
-                                    acc[i][k].y += xs[i].x * ys[k].y + xs[i].y * ys[k].x;
+                                for (int q = 0; q < 4; ++q) acc[i][k][q] = 0.f;
+                        for (int c0 = b; c0 < e; c0 += CH) {
+                            const int nc = e - c0 < CH ? e - c0 : CH;
+                            cx.sync();
+                            for (int w = tid; w < nc * (TX + TY); w += kThreads) {
+                                const int a = w / (TX + TY), r = w % (TX + TY);
+                                if (r < TX) {
+                                    const int g = kx0 + r;
+                                    float2 z = unit_phase(g, ux[c0 + a]);          // (c, -s)
+                                    z.y = -z.y;
+                                    if (g == 0 && nq_x) {
+                                        const float2 n = unit_phase(p.nx / 2, ux[c0 + a]);
+                                        z.y = n.x;
+                                        snx[a] = n.y;
+                                    }
+                                    ex[a * TX + r] = z;
+                                } else {
+                                    const int g = ky0 + r - TX;
+                                    float2 z = unit_phase(g, uy[c0 + a]);
+                                    z.y = -z.y;
+                                    if (g == 0 && nq_y) {
+                                        const float2 n = unit_phase(p.ny / 2, uy[c0 + a]);
+                                        z.y = n.x;
+                                        sny[a] = n.y;
+                                    }
+                                    ey[a * TY + r - TX] = z;
                                 }
+                            }
+                            cx.sync();
+                            for (int a = 0; a < nc; ++a) {
+                                float2 xs[4], ys[2];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) xs[i] = ex[a * TX + ty + 16 * i];
+#pragma unroll
+                                for (int k = 0; k < 2; ++k) ys[k] = ey[a * TY + tx + 16 * k];
+#pragma unroll
+                                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                                    for (int k = 0; k < 2; ++k) {
+                                        acc[i][k][0] += xs[i].x * ys[k].x;
+                                        acc[i][k][1] += xs[i].y * ys[k].y;
+                                        acc[i][k][2] += xs[i].x * ys[k].y;
+                                        acc[i][k][3] += xs[i].y * ys[k].x;
+                                    }
+                            }
+                            if (corner_tile)                        // block-uniform
+                                for (int a = 0; a < nc; ++a) corr += snx[a] * sny[a];
                         }
-                        if (corner_tile) {                         // block-uniform: Re(ex*ey) = cos*cos - sin*sin
-                            for (int a = 0; a < nc; ++a) corr += snx[a] * sny[a];
-                        }
+                        const float* ff = p.ff + (long long)t * p.nx * p.ny;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                if (gx[i] < nsx && gy[k] < nsy) {
+                                    // row / column of the form-factor table for the cosine and the "sine" component
+                                    const int fx0 = gx[i], fx1 = (gx[i] == 0 && nq_x) ? p.nx / 2 : gx[i];
+                                    const int fy0 = gy[k], fy1 = (gy[k] == 0 && nq_y) ? p.ny / 2 : gy[k];
+                                    float ss = acc[i][k][1];
+                                    if (corner_tile && gx[i] == 0 && gy[k] == 0) ss -= corr;
+                                    tot[i][k][0] += acc[i][k][0] * __ldg(&ff[(long long)fx0 * p.ny + fy0]);
+                                    tot[i][k][1] += ss * __ldg(&ff[(long long)fx1 * p.ny + fy1]);
+                                    tot[i][k][2] += acc[i][k][2] * __ldg(&ff[(long long)fx0 * p.ny + fy1]);
+                                    tot[i][k][3] += acc[i][k][3] * __ldg(&ff[(long long)fx1 * p.ny + fy0]);
+                                }
+                            }
                     }
-                    const float* ff = p.ff + (long long)t * p.nx * p.ny;
+                }
+                if (h == 0) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
 #pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            if (kxs[i] < p.nx && kys[k] < nyh) {
-                                const float w = __ldg(&ff[(long long)kxs[i] * p.ny + kys[k]]);
-                                float re = acc[i][k].x;
-                                if (kxs[i] == nyq_x && kys[k] == nyq_y) re -= corr;
-                                tot[h][i][k].x += re * w;
-                                tot[h][i][k].y += acc[i][k].y * w;
-                            }
-                        }
+                        for (int k = 0; k < 2; ++k)
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) stash[((i * 2 + k) * 4 + q) * kThreads + tid] = tot[i][k][q];
                 }
             }
-            // Z[k] = A + iB,  Z[-k] = conj(A) + i*conj(B)
-            float2* out = p.out + ((long long)f * p.npairs + m) * p.nx * p.ny;
+            // tot = second slice (B), stash = first slice (A):  Z = S'_A + i*S'_B at up to four mirror positions
+            float2* out = p.out + ((long long)f * p.pair_count + ml) * p.nx * p.ny;
+            auto emit = [&](int kx, int ky, float ar, float ai, float br, float bi) {
+                out[(long long)kx * p.ny + ky] = make_float2(ar - bi, ai + br);
+            };
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int k = 0; k < 2; ++k) {
-                    const int kx = kxs[i], ky = kys[k];
-                    if (kx < p.nx && ky < nyh) {
-                        const float2 A = tot[0][i][k], B = tot[1][i][k];
-                        out[(long long)kx * p.ny + ky] = make_float2(A.x - B.y, A.y + B.x);
-                        const int my = ky == 0 ? 0 : p.ny - ky;
-                        if (my >= nyh) {
-                            const int mx = kx == 0 ? 0 : p.nx - kx;
-                            out[(long long)mx * p.ny + my] = make_float2(A.x + B.y, B.x - A.y);
+                    const int x = gx[i], y = gy[k];
+                    if (x >= nsx || y >= nsy) continue;
+                    float A[4], B[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        A[q] = stash[((i * 2 + k) * 4 + q) * kThreads + tid];
+                        B[q] = tot[i][k][q];
+                    }
+                    const float acc_ = A[0], ass = A[1], acs = A[2], asc = A[3];
+                    const float bcc = B[0], bss = B[1], bcs = B[2], bsc = B[3];
+                    if (x > 0 && y > 0) {
+                        emit(x, y, acc_ - ass, -(acs + asc), bcc - bss, -(bcs + bsc));
+                        emit(p.nx - x, y, acc_ + ass, -(acs - asc), bcc + bss, -(bcs - bsc));
+                        emit(x, p.ny - y, acc_ + ass, acs - asc, bcc + bss, bcs - bsc);
+                        emit(p.nx - x, p.ny - y, acc_ - ass, acs + asc, bcc - bss, bcs + bsc);
+                    } else if (x == 0 && y > 0) {
+                        emit(0, y, acc_, -acs, bcc, -bcs);
+                        emit(0, p.ny - y, acc_, acs, bcc, bcs);
+                        if (nq_x) {
+                            emit(p.nx / 2, y, asc, -ass, bsc, -bss);
+                            emit(p.nx / 2, p.ny - y, asc, ass, bsc, bss);
                         }
+                    } else if (x > 0 && y == 0) {
+                        emit(x, 0, acc_, -asc, bcc, -bsc);
+                        emit(p.nx - x, 0, acc_, asc, bcc, bsc);
+                        if (nq_y) {
+                            emit(x, p.ny / 2, acs, -ass, bcs, -bss);
+                            emit(p.nx - x, p.ny / 2, acs, ass, bcs, bss);
+                        }
+                    } else {
+                        emit(0, 0, acc_, 0.f, bcc, 0.f);
+                        if (nq_y) emit(0, p.ny / 2, acs, 0.f, bcs, 0.f);
+                        if (nq_x) emit(p.nx / 2, 0, asc, 0.f, bsc, 0.f);
+                        if (nq_x && nq_y) emit(p.nx / 2, p.ny / 2, ass, 0.f, bss, 0.f);
                     }
                 }
         }

@@ -19,8 +19,9 @@ from . import _lib, hostmath
 PSI_BATCH_BYTES = 48 << 20
 # Upper bound for the transmission-function buffer of one frame batch.
 T_BATCH_BYTES = 24 << 30
-# Workspace of the potential build (slice-paired spectra); frames are chunked to fit it.
-SCRATCH_BYTES = 2 << 30
+# Workspace of the potential build (slice-paired spectra): chunks of this size flow through the three
+# potential kernels while staying L2-resident.
+SCRATCH_BYTES = 32 << 20
 
 
 class PhaseTimer:
@@ -197,8 +198,8 @@ def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential:
     t = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device=dev)
     V = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev) if want_potential else None
     scale = 1.0 / (plan.dx ** 2 * plan.dy ** 2)
-    per_frame = ((plan.nz + 1) // 2) * plan.nx * plan.ny
-    n_scratch = per_frame * max(1, min(F, SCRATCH_BYTES // (8 * per_frame)))
+    img = plan.nx * plan.ny
+    n_scratch = img * max(1, min(F * ((plan.nz + 1) // 2), SCRATCH_BYTES // (8 * img)))
     if scratch is None or scratch.numel() < n_scratch:
         scratch = torch.empty((n_scratch,), dtype=torch.complex64, device=dev)
     L = _lib.lib()

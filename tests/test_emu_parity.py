@@ -130,3 +130,21 @@ def test_layers_and_propagate_api():
     psi = Propagate(probe, pot)
     ref = orc.propagate(np.ones((64, 64)), V, xs, ys, zs, 100e3)[0]
     assert rel_l2(psi.numpy(), ref) < 1e-4
+
+
+def test_potential_chunking_is_bitwise_invariant():
+    """the potential build streams slice-pair images through an L2-sized scratch; any chunking
+    (pairs split within a frame, several frames per chunk) must give identical bits"""
+    from pyslice_b200 import engine, hostmath
+    traj = small64_traj()
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    pos = torch.from_numpy(traj.positions.copy())
+    ref = engine.build_transmission(plan, pos)
+    old = engine.SCRATCH_BYTES
+    try:
+        for nimg in (1, 3, 11):
+            engine.SCRATCH_BYTES = 64 * 64 * 8 * nimg
+            assert torch.equal(engine.build_transmission(plan, pos), ref)
+    finally:
+        engine.SCRATCH_BYTES = old
