@@ -42,6 +42,9 @@ int psb_sm_count(void);
 void psb_release_tables(void);
 /* kernels launched by this library in this process so far (benchmark bookkeeping) */
 long long psb_launch_count(void);
+/* diagnostic switch: 0 routes the steady-state slice step through the generic line-pass kernels instead of
+ * the fused persistent kernels (both are CUDA; used by microbenchmarks and A/B parity tests). Default 1. */
+void psb_set_fast_path(int enable);
 
 /* ---- atom -> slice binning: src/multislice/potentials.py:297-317 (+ bounds :304-305) -------------
  * positions (F, A, 3) float64; type_idx (A) dense type index in [0, ntypes);

@@ -1,6 +1,7 @@
 // C ABI of libpsb.so: argument checking and kernel orchestration (see include/pyslice_b200.h).
 #include "../../include/pyslice_b200.h"
 
+#include "fast_path.h"
 #include "line_pass.cuh"
 #include "potential_kernels.cuh"
 #include "psb_rt.h"
@@ -59,6 +60,13 @@ const char* psb_last_error(void) { return last_error(); }
 int psb_sm_count(void) { return rt::sm_count(); }
 void psb_release_tables(void) { free_all_tables(); }
 long long psb_launch_count(void) { return launch_counter(); }
+void psb_set_fast_path(int enable) {
+#ifndef PSB_EMU
+    fast_path_enable(enable);
+#else
+    (void)enable;
+#endif
+}
 
 int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames, int n_atoms, int ntypes,
                   int nz, const double* lo, const double* hi, double dz, double lx_eff, double ly_eff,
@@ -239,11 +247,23 @@ int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_p
     ex.out_stride_probe = stride_probe; ex.out_stride_frame = stride_frame;
     ex.out_elem_stride = ny; ex.out_line_stride = 1;
 
+#ifndef PSB_EMU
+    // fused persistent kernels for the steady state (fast_path.cu); the propagator is split Px -> column pass,
+    // Py -> next row pass, which is exact because no propagation follows the last slice
+    const bool fast = fast_slice_supported(nx, ny);
+#else
+    const bool fast = false;
+#endif
     int layer = 0;
     for (int z = 0; z < nz; ++z) {
         row.mul = f2(t) + (long long)z * img;
         int rc;
-        if (z == 0) {
+        if (z > 0 && fast) {
+#ifndef PSB_EMU
+            rc = launch_fast_rows(f2(psi_work), n_img, nx, ny, f2(t) + (long long)z * img, (long long)nz * img, n_probes,
+                                  f2(prop_y), s);
+#endif
+        } else if (z == 0) {
             row.src = f2(probes); row.src_img_stride = img; row.src_img_mod = n_probes;
             rc = launch_line_pass(PASS_R1, row, n_img, s);
         } else {
@@ -260,6 +280,10 @@ int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_p
             ++layer;
         }
         if (!last) {
+#ifndef PSB_EMU
+            if (fast) rc = launch_fast_cols(f2(psi_work), n_img, nx, ny, f2(prop_x), s);
+            else
+#endif
             rc = launch_line_pass(PASS_C, col, n_img, s);
             if (rc != PSB_OK) return rc;
         }

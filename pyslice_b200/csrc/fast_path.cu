@@ -1,1 +1,414 @@
-// placeholder for the fused persistent slice-step kernels (filled in by the optimisation milestone)
+// Fused slice-step kernels for 256- and 512-point lines: the steady state of psb_propagate
+// (reference: src/multislice/multislice.py:281-294, one loop iteration = one row pass + one column pass).
+//
+//   row pass   psi[x, ky] -> FFT_y( t_s[x, y] * IFFT_y( Py[ky] * psi[x, ky] ) )        (in place)
+//   col pass   psi[x, ky] -> IFFT_x( Px[kx] * FFT_x( psi[x, ky] ) )                     (in place)
+//
+// with the Fresnel propagator split as P[kx, ky] = Px[kx] * Py[ky] (Py commutes with the x transforms, so
+// it is applied where ky runs along the line).  Both are persistent kernels sized to the SM count:
+//
+//   * inputs arrive through the async proxy: cp.async.bulk (TMA, 1-D) global -> shared, completion on an
+//     mbarrier; the copy for the NEXT tile is issued as soon as the current tile's landing buffer has been
+//     read into registers, so L2/HBM latency hides behind the two line FFTs of the current tile;
+//   * row pass: a line (2 KB / 4 KB) belongs to the 16 / 32 lanes of ONE warp, so every warp is its own
+//     pipeline (private landing + exchange buffers, private mbarriers, __syncwarp only; no CTA barrier in
+//     the loop); 16 warps per SM;
+//   * column pass: a tile is 16 (8 for N = 512) adjacent columns so global segments are 128 B (64 B);
+//     256 threads, one CTA barrier per FFT stage exchange thanks to two alternating exchange buffers;
+//     2 CTAs per SM;
+//   * arithmetic is packed fp32x2 with per-thread persistent twiddles (fast_fft.cuh); the propagator
+//     factors sit in shared memory for the whole kernel.
+//
+// Algorithmic traffic per slice step and image: psi is read and written once per pass (L2-resident for the
+// batch sizes engine.py picks), t is read once from HBM by the row pass.
+#include "fast_fft.cuh"
+#include "fast_path.h"
+#include "psb_rt.h"
+#include "tables.h"
+
+#include <cuda.h>
+
+#include <atomic>
+#include <string>
+
+namespace psb {
+
+namespace {
+
+std::atomic<int> g_fast_enabled{1};
+
+// ---- async-proxy plumbing (PTX) --------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n"
+        " bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// 2-D tiled tensor copy (TMA): box of the tensor map at element coordinates (c0 = column, c1 = row)
+__device__ __forceinline__ void tensor2d_g2s(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ---- row pass ------------------------------------------------------------------------------------------
+struct RowPassParams {
+    float2* psi;                 // (n_img, nx, N) contiguous, transformed in place
+    const float2* t;             // transmission slice of frame 0 (already offset to slice z)
+    long long t_frame_stride;    // elements between consecutive frames of t
+    int probes;                  // images per frame (image = frame*probes + probe)
+    int nx;                      // lines per image
+    const float2* py;            // [N] propagator factor along the line
+    const float2* tw;            // staged twiddle table of Plan<N, 16>
+    long long n_units;           // n_img * nx / lines-per-warp
+};
+
+template <int N>
+struct RowCfg {
+    static constexpr int T = N / 16;               // threads per line
+    static constexpr int LPW = 32 / T;             // lines per warp
+    static constexpr int NP = N + N / 16;          // padded exchange pitch
+    static constexpr int kWarps = 16;
+    static constexpr int kLand = LPW * N;          // float2 per landing buffer (4 KB)
+    static constexpr int kX = LPW * NP;
+    static constexpr int kWarpElems = 2 * kLand + kX;
+    static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + (size_t)N * sizeof(float2) + kWarps * 2 * sizeof(uint64_t);
+    static constexpr uint32_t kBytes = kLand * sizeof(float2);
+};
+
+template <int N>
+struct RowXchg {
+    float2* x;
+    int c;
+    __device__ __forceinline__ float2* buf(int) const { return x; }
+    __device__ __forceinline__ int at(int q) const { return c * RowCfg<N>::NP + q + (q >> 4); }
+    __device__ __forceinline__ void after_store(int) const { __syncwarp(); }
+    __device__ __forceinline__ void after_load(int) const { __syncwarp(); }
+};
+
+template <int N>
+__global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p) {
+    using C = RowCfg<N>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: bulk copies take uniform operands
+    const int lane = threadIdx.x & 31;
+    float2* land_psi = sm + (size_t)warp * C::kWarpElems;
+    float2* land_t = land_psi + C::kLand;
+    float2* xb = land_t + C::kLand;
+    float2* spy = sm + (size_t)C::kWarps * C::kWarpElems;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(spy + N) + 2 * warp;
+    uint64_t* mb_psi = bars;
+    uint64_t* mb_t = bars + 1;
+
+    if (lane == 0) {
+        mbar_init(mb_psi, 1);
+        mbar_init(mb_t, 1);
+        mbar_init_fence();
+    }
+    for (int i = threadIdx.x; i < N; i += blockDim.x) spy[i] = p.py[i];
+    __syncthreads();
+
+    const int c = lane / C::T, j = lane % C::T;
+    fast::Twiddles<N> tw;
+    tw.load(p.tw, j);
+    const RowXchg<N> xc{xb, c};
+
+    const long long GW = (long long)gridDim.x * C::kWarps;
+    long long u = (long long)blockIdx.x * C::kWarps + warp;
+    const int units_per_img = p.nx / C::LPW;
+
+    auto issue = [&](long long unit, bool want_psi, bool want_t) {
+        if (want_psi) {
+            mbar_expect_tx(mb_psi, C::kBytes);
+            bulk_g2s(land_psi, p.psi + unit * C::kLand, C::kBytes, mb_psi);
+        }
+        if (want_t) {
+            const long long img = unit / units_per_img;
+            const long long row0 = (unit % units_per_img) * C::LPW;
+            const float2* src = p.t + (img / p.probes) * p.t_frame_stride + row0 * N;
+            mbar_expect_tx(mb_t, C::kBytes);
+            bulk_g2s(land_t, src, C::kBytes, mb_t);
+        }
+    };
+    if (u < p.n_units && lane == 0) issue(u, true, true);
+
+    for (uint32_t it = 0; u < p.n_units; u += GW, ++it) {
+        const uint32_t parity = it & 1u;
+        const long long un = u + GW;
+        const bool next = un < p.n_units;
+        float2 v[16];
+        mbar_wait(mb_psi, parity);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(land_psi[c * N + j + e * C::T], spy[j + e * C::T]);
+        __syncwarp();
+        if (lane == 0 && next) issue(un, true, false);
+        fast::line_fft<N, +1>(v, tw, j, xc, 0);
+        mbar_wait(mb_t, parity);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], land_t[c * N + j + e * C::T]);
+        __syncwarp();
+        if (lane == 0 && next) issue(un, false, true);
+        fast::line_fft<N, -1>(v, tw, j, xc, 0);
+        float2* dst = p.psi + u * C::kLand + c * N + j;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dst[e * C::T] = v[e];
+    }
+}
+
+// ---- column pass ---------------------------------------------------------------------------------------
+struct ColPassParams {
+    float2* psi;                 // (n_img, N, NY) contiguous, transformed in place along the first image axis
+    const float2* px;            // [N] propagator factor along the line (includes 1/(nx*ny))
+    const float2* tw;
+    long long n_tiles;           // n_img * NY / W
+};
+
+template <int N>
+struct ColCfg {
+    static constexpr int T = N / 16;
+    static constexpr int W = 256 / T;                                 // columns per tile: 16 (N=256), 8 (N=512)
+    static constexpr int kPadRows = (W == 8) ? N / 16 : 0;            // keeps 8-column rows conflict-free
+    static constexpr int kLand = N * W;                               // float2 (32 KB)
+    static constexpr int kX = (N + kPadRows) * W;
+    static constexpr size_t kSmem = (size_t)(kLand + 2 * kX + N) * sizeof(float2) + 2 * sizeof(uint64_t);
+    static constexpr int kBoxRows = 256;                              // TMA box limit per dimension
+    static constexpr uint32_t kBytes = kLand * sizeof(float2);
+};
+
+// Exchange policy of the column pass: two alternating buffers, one CTA barrier per exchange.  The first
+// barrier of a tile doubles as the "landing buffer is free" point: thread 0 then issues the next tile's TMA.
+template <int N>
+struct ColXchg {
+    float2* b0;
+    float2* b1;
+    int c;
+    const CUtensorMap* map;
+    uint64_t* mb;
+    float2* land;
+    int next_c0, next_r0;        // tensor coordinates of the next tile; next_c0 < 0: nothing to prefetch
+    __device__ __forceinline__ float2* buf(int i) const { return (i & 1) ? b1 : b0; }
+    __device__ __forceinline__ int at(int q) const {
+        return (ColCfg<N>::W == 8 ? q + (q >> 4) : q) * ColCfg<N>::W + c;
+    }
+    __device__ __forceinline__ void after_store(int i) const {
+        __syncthreads();
+        if (i == 0 && next_c0 >= 0 && threadIdx.x == 0) {
+            mbar_expect_tx(mb, ColCfg<N>::kBytes);
+#pragma unroll
+            for (int h = 0; h < N / ColCfg<N>::kBoxRows; ++h)
+                tensor2d_g2s(land + h * ColCfg<N>::kBoxRows * ColCfg<N>::W, map, next_c0, next_r0 + h * ColCfg<N>::kBoxRows, mb);
+        }
+    }
+    __device__ __forceinline__ void after_load(int) const {}
+};
+
+template <int N, int NY>
+__global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant__ CUtensorMap tmap, const ColPassParams p) {
+    using C = ColCfg<N>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* land = reinterpret_cast<float2*>(smem_raw);
+    float2* xb0 = land + C::kLand;
+    float2* xb1 = xb0 + C::kX;
+    float2* spx = xb1 + C::kX;
+    uint64_t* mb = reinterpret_cast<uint64_t*>(spx + N);
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mbar_init(mb, 1);
+        mbar_init_fence();
+    }
+    for (int i = tid; i < N; i += 256) spx[i] = p.px[i];
+    __syncthreads();
+
+    const int c = tid % C::W, j = tid / C::W;
+    fast::Twiddles<N> tw;
+    tw.load(p.tw, j);
+    constexpr int kTilesPerImg = NY / C::W;
+
+    long long tile = blockIdx.x;
+    const long long G = gridDim.x;
+    ColXchg<N> xc{xb0, xb1, c, &tmap, mb, land, -1, 0};
+    if (tile < p.n_tiles && tid == 0) {
+        mbar_expect_tx(mb, C::kBytes);
+#pragma unroll
+        for (int h = 0; h < N / C::kBoxRows; ++h)
+            tensor2d_g2s(land + h * C::kBoxRows * C::W, &tmap, (int)(tile % kTilesPerImg) * C::W,
+                         (int)(tile / kTilesPerImg) * N + h * C::kBoxRows, mb);
+    }
+    for (uint32_t it = 0; tile < p.n_tiles; tile += G, ++it) {
+        const long long nt = tile + G;
+        if (nt < p.n_tiles) {
+            xc.next_c0 = (int)(nt % kTilesPerImg) * C::W;
+            xc.next_r0 = (int)(nt / kTilesPerImg) * N;
+        } else {
+            xc.next_c0 = -1;
+        }
+        mbar_wait(mb, it & 1u);
+        float2 v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = land[(j + e * C::T) * C::W + c];
+        fast::line_fft<N, -1>(v, tw, j, xc, 0);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], spx[j + e * C::T]);
+        xc.next_c0 = -1;
+        fast::line_fft<N, +1>(v, tw, j, xc, fast::exchanges<N>());
+        float2* dst = p.psi + (tile / kTilesPerImg) * ((long long)N * NY) + (tile % kTilesPerImg) * C::W + j * NY + c;
+#pragma unroll
+        for (int e = 0; e < 16; ++e) dst[e * C::T * NY] = v[e];
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+template <class K>
+int ensure_smem(K kernel, size_t bytes, const char* what) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return PSB_OK;
+}
+
+int twiddles_for(int n, const float2** tw, cudaStream_t s) {
+    FftTables tb;
+    int N = 0;
+    bool blue = false;
+    int rc = get_fft_tables(n, &tb, &N, &blue, s);
+    if (rc != PSB_OK) return rc;
+    if (blue || N != n) return fail(PSB_ERR_UNSUPPORTED, "fast path needs a power-of-two line");
+    *tw = tb.tw;
+    return PSB_OK;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not a link-time dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_cols_map(CUtensorMap* map, float2* psi, long long rows_total, int ny, int box_cols, int box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q);
+        if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !ptr)
+            return fail(PSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    // psi as a 2-D tensor of 8-byte elements: dim0 = column (ny), dim1 = row over all images
+    const cuuint64_t gdim[2] = {(cuuint64_t)ny, (cuuint64_t)rows_total};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ny * sizeof(float2)};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, psi, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PSB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return PSB_OK;
+}
+
+template <int N>
+int rows_go(const RowPassParams& p, cudaStream_t s) {
+    using C = RowCfg<N>;
+    static bool ready = false;
+    if (!ready) {
+        int rc = ensure_smem(fast_rows_kernel<N>, C::kSmem, "fast row pass");
+        if (rc != PSB_OK) return rc;
+        ready = true;
+    }
+    long long want = (p.n_units + C::kWarps - 1) / C::kWarps;
+    const int sms = rt::sm_count();
+    const int grid = (int)(want < sms ? want : sms);
+    fast_rows_kernel<N><<<grid, 512, C::kSmem, s>>>(p);
+    ++launch_counter();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast row pass launch: ") + cudaGetErrorString(e));
+    return PSB_OK;
+}
+
+template <int N, int NY>
+int cols_go(float2* psi, int n_img, const float2* px, const float2* tw, cudaStream_t s) {
+    using C = ColCfg<N>;
+    static bool ready = false;
+    if (!ready) {
+        int rc = ensure_smem(fast_cols_kernel<N, NY>, C::kSmem, "fast column pass");
+        if (rc != PSB_OK) return rc;
+        ready = true;
+    }
+    // the tensor map depends on the buffer and the batch size only: keep the last one
+    static CUtensorMap map;
+    static float2* map_psi = nullptr;
+    static int map_img = -1;
+    if (map_psi != psi || map_img != n_img) {
+        int rc = encode_cols_map(&map, psi, (long long)n_img * N, NY, C::W, C::kBoxRows);
+        if (rc != PSB_OK) return rc;
+        map_psi = psi;
+        map_img = n_img;
+    }
+    ColPassParams p;
+    p.psi = psi; p.px = px; p.tw = tw;
+    p.n_tiles = (long long)n_img * (NY / C::W);
+    const long long slots = 2LL * rt::sm_count();
+    const int grid = (int)(p.n_tiles < slots ? p.n_tiles : slots);
+    fast_cols_kernel<N, NY><<<grid, 256, C::kSmem, s>>>(map, p);
+    ++launch_counter();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast column pass launch: ") + cudaGetErrorString(e));
+    return PSB_OK;
+}
+
+}  // namespace
+
+void fast_path_enable(int on) { g_fast_enabled.store(on ? 1 : 0); }
+
+bool fast_slice_supported(int nx, int ny) {
+    if (!g_fast_enabled.load()) return false;
+    return (nx == 256 || nx == 512) && (ny == 256 || ny == 512);
+}
+
+int launch_fast_rows(float2* psi, int n_img, int nx, int ny, const float2* t_slice, long long t_frame_stride,
+                     int probes, const float2* py, cudaStream_t s) {
+    RowPassParams p;
+    p.psi = psi; p.t = t_slice; p.t_frame_stride = t_frame_stride; p.probes = probes; p.nx = nx; p.py = py;
+    int rc = twiddles_for(ny, &p.tw, s);
+    if (rc != PSB_OK) return rc;
+    if (ny == 256) {
+        p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
+        return rows_go<256>(p, s);
+    }
+    p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
+    return rows_go<512>(p, s);
+}
+
+int launch_fast_cols(float2* psi, int n_img, int nx, int ny, const float2* px, cudaStream_t s) {
+    const float2* tw = nullptr;
+    int rc = twiddles_for(nx, &tw, s);
+    if (rc != PSB_OK) return rc;
+    if (nx == 256 && ny == 256) return cols_go<256, 256>(psi, n_img, px, tw, s);
+    if (nx == 256 && ny == 512) return cols_go<256, 512>(psi, n_img, px, tw, s);
+    if (nx == 512 && ny == 256) return cols_go<512, 256>(psi, n_img, px, tw, s);
+    if (nx == 512 && ny == 512) return cols_go<512, 512>(psi, n_img, px, tw, s);
+    return fail(PSB_ERR_UNSUPPORTED, "fast column pass: unsupported grid");
+}
+
+}  // namespace psb

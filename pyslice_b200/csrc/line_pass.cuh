@@ -64,7 +64,11 @@ template <int N, int E, int W, bool COLS, bool BLUE, int F1, int MID, int F2, in
 struct LinePass {
     static constexpr int T = N / E;
     static constexpr int kThreads = W * T;
+#ifdef PSB_LP_MINBLOCKS
+    static constexpr int kMinBlocks = PSB_LP_MINBLOCKS;     // tuning experiments only (tools/)
+#else
     static constexpr int kMinBlocks = (512 / kThreads) > 0 ? (512 / kThreads) : 1;
+#endif
     using Map = SmemMap<N, W, COLS>;
     static constexpr size_t kSmem = Map::kBytes;
 

@@ -77,6 +77,12 @@ def launch_count() -> int:
     return int(_lib.lib().psb_launch_count())
 
 
+def set_fast_path(enable: bool) -> None:
+    """Diagnostic switch: route the steady-state slice step through the fused persistent kernels (default) or
+    through the generic line-pass kernels.  Both are CUDA; used by A/B parity tests and microbenchmarks."""
+    _lib.lib().psb_set_fast_path(1 if enable else 0)
+
+
 def _device(device=None) -> torch.device:
     if _lib.is_emulated():                       # tests/emu only
         return torch.device("cpu")
@@ -295,18 +301,42 @@ def sum_frames(x: torch.Tensor) -> torch.Tensor:
     return out
 
 
+def _sm_count() -> int:
+    return int(_lib.lib().psb_sm_count()) if not _lib.is_emulated() else 148
+
+
+def _fill_images(max_imgs: int, tiles_per_img: int, slots: int) -> int:
+    """Largest image count <= max_imgs whose tiles fill whole rounds of the persistent grids best: the
+    slice-step kernels run `slots` tile pipelines side by side, so n images cost ceil(n*tiles/slots) rounds."""
+    best, best_eff = max_imgs, 0.0
+    for n in range(max_imgs, max(0, max_imgs // 2), -1):
+        work = n * tiles_per_img
+        eff = work / (-(-work // slots) * slots)
+        if eff > best_eff + 1e-9:
+            best, best_eff = n, eff
+    return best
+
+
 def batch_sizes(plan: SlicePlan, n_probes: int, n_frames: int):
-    """(frames per batch, probes per sub-batch) so the psi batch stays L2-resident and the
-    transmission buffer stays bounded."""
+    """(frames per batch, probes per sub-batch) so the psi batch stays L2-resident, the transmission buffer
+    stays bounded, the image count fills the persistent slice-step grids, and batches are balanced."""
     img = plan.nx * plan.ny * 8
     per_frame_t = plan.nz * img
     max_imgs = max(1, PSI_BATCH_BYTES // img)
+    slots = 2 * _sm_count()
+    tiles_per_img = max(1, plan.ny // (8 if plan.nx >= 512 else 16))
     if n_probes >= max_imgs:
-        fb, pb = 1, max_imgs
+        fb, pb = 1, _fill_images(max_imgs, tiles_per_img, slots)
+        n_sub = -(-n_probes // pb)
+        pb = -(-n_probes // n_sub)                    # balanced probe sub-batches
     else:
-        fb, pb = max(1, max_imgs // n_probes), n_probes
-    fb = min(fb, max(1, T_BATCH_BYTES // per_frame_t), max(1, 65535 // plan.nz), n_frames)
-    if plan.device.type == "cuda":
-        free, _ = torch.cuda.mem_get_info(plan.device)
-        fb = max(1, min(fb, int(free * 0.5) // per_frame_t))
+        fb_cap = max(1, max_imgs // n_probes)
+        fb_cap = min(fb_cap, max(1, T_BATCH_BYTES // per_frame_t), max(1, 65535 // plan.nz), n_frames)
+        if plan.device.type == "cuda":
+            free, _ = torch.cuda.mem_get_info(plan.device)
+            fb_cap = max(1, min(fb_cap, int(free * 0.5) // per_frame_t))
+        fb = max(1, _fill_images(fb_cap * n_probes, tiles_per_img, slots) // n_probes) if fb_cap < n_frames else fb_cap
+        n_batches = -(-n_frames // fb)
+        fb = -(-n_frames // n_batches)                # balanced frame batches
+        pb = n_probes
     return fb, min(pb, 65535 // max(1, fb))
