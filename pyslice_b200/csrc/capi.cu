@@ -58,7 +58,12 @@ extern "C" {
 int psb_version(void) { return 100; }
 const char* psb_last_error(void) { return last_error(); }
 int psb_sm_count(void) { return rt::sm_count(); }
-void psb_release_tables(void) { free_all_tables(); }
+void psb_release_tables(void) {
+    free_all_tables();
+#ifndef PSB_EMU
+    sf_fast_release();
+#endif
+}
 long long psb_launch_count(void) { return launch_counter(); }
 void psb_set_fast_path(int enable) {
 #ifndef PSB_EMU
@@ -142,9 +147,26 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
             if (groups > nm) groups = nm;
             sp.pairs_per_block = (int)((nm + groups - 1) / groups);
             groups = (nm + sp.pairs_per_block - 1) / sp.pairs_per_block;
-            int rc = go<StructureFactorPaired>(dim3(tiles, (unsigned)groups, nf), StructureFactorPaired::kSmem, s, sp, "structure_factor");
+            int rc;
+#ifndef PSB_EMU
+            if (fast_path_enabled())
+                rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, formfactors, f2(scratch), s);
+            else
+#endif
+            rc = go<StructureFactorPaired>(dim3(tiles, (unsigned)groups, nf), StructureFactorPaired::kSmem, s, sp, "structure_factor");
             if (rc != PSB_OK) return rc;
 
+#ifndef PSB_EMU
+            if (fast_slice_supported(nx, ny)) {      // persistent TMA kernels (fast_path.cu), same arithmetic
+                rc = launch_fast_cols_inverse(f2(scratch), nf * nm, nx, ny, s);
+                if (rc != PSB_OK) return rc;
+                rc = launch_fast_rows_transmit(f2(scratch), nf * nm, nx, ny, scale / ((float)nx * (float)ny), sigma,
+                                               f2(t_out) + (long long)f0 * nz * img,
+                                               v_out ? v_out + (long long)f0 * nz * img : nullptr, nm, nz, mb, s);
+                if (rc != PSB_OK) return rc;
+                continue;
+            }
+#endif
             PassParams p = base_params();
             p.src = f2(scratch); p.dst = f2(scratch); p.src_img_stride = img; p.dst_img_stride = img;
             cols_geometry(p, nx, ny);

@@ -21,93 +21,115 @@ namespace psb {
 namespace fast {
 
 // ---- packed complex arithmetic ----------------------------------------------------------------
+// On the device a complex number lives in ONE 64-bit register pair (`cpx` = b64) from load to store, so
+// ptxas never has to re-pair the halves (a float2 round trip through st.v2.f32 serialised every store
+// through one register pair -- ncu r1d); on the host (tests) it is a plain float2.
 #if defined(__CUDA_ARCH__)
-#define PSB_U64(x) (*reinterpret_cast<unsigned long long*>(&(x)))
-PSB_D float2 add2(float2 a, float2 b) {
-    float2 d;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(PSB_U64(d)) : "l"(PSB_U64(a)), "l"(PSB_U64(b)));
+typedef unsigned long long cpx;
+PSB_D cpx c_make(float x, float y) {
+    cpx d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(x), "f"(y));
     return d;
 }
-PSB_D float2 sub2(float2 a, float2 b) {
-    float2 d;
-    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(PSB_U64(d)) : "l"(PSB_U64(a)), "l"(PSB_U64(b)));
+PSB_D float c_re(cpx a) {
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+    return x;
+}
+PSB_D float c_im(cpx a) {
+    float x, y;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(a));
+    return y;
+}
+PSB_D cpx add2(cpx a, cpx b) {
+    cpx d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-PSB_D float2 mul2(float2 a, float2 b) {
-    float2 d;
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(PSB_U64(d)) : "l"(PSB_U64(a)), "l"(PSB_U64(b)));
+PSB_D cpx sub2(cpx a, cpx b) {
+    cpx d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-PSB_D float2 fma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(PSB_U64(d)) : "l"(PSB_U64(a)), "l"(PSB_U64(b)), "l"(PSB_U64(c)));
+PSB_D cpx mul2(cpx a, cpx b) {
+    cpx d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
-#undef PSB_U64
+PSB_D cpx fma2(cpx a, cpx b, cpx c) {
+    cpx d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
 #else
-PSB_D float2 add2(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-PSB_D float2 sub2(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-PSB_D float2 mul2(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
-PSB_D float2 fma2(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+typedef float2 cpx;
+PSB_D cpx c_make(float x, float y) { return make_float2(x, y); }
+PSB_D float c_re(cpx a) { return a.x; }
+PSB_D float c_im(cpx a) { return a.y; }
+PSB_D cpx add2(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
+PSB_D cpx sub2(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
+PSB_D cpx mul2(cpx a, cpx b) { return make_float2(a.x * b.x, a.y * b.y); }
+PSB_D cpx fma2(cpx a, cpx b, cpx c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
 #endif
+static_assert(sizeof(cpx) == sizeof(float2), "cpx is a bit-cast of float2");
 
 // a * w
-PSB_D float2 cmulp(float2 a, float2 w) {
-    return fma2(make_float2(-a.y, a.x), make_float2(w.y, w.y), mul2(a, make_float2(w.x, w.x)));
+PSB_D cpx cmulp(cpx a, cpx w) {
+    return fma2(c_make(-c_im(a), c_re(a)), c_make(c_im(w), c_im(w)), mul2(a, c_make(c_re(w), c_re(w))));
 }
 // a * conj(w)
-PSB_D float2 cmulcp(float2 a, float2 w) {
-    return fma2(make_float2(a.y, -a.x), make_float2(w.y, w.y), mul2(a, make_float2(w.x, w.x)));
+PSB_D cpx cmulcp(cpx a, cpx w) {
+    return fma2(c_make(c_im(a), -c_re(a)), c_make(c_im(w), c_im(w)), mul2(a, c_make(c_re(w), c_re(w))));
 }
 // a - i*b  and  a + i*b
-PSB_D float2 sub_ib(float2 a, float2 b) { return fma2(make_float2(b.y, b.x), make_float2(1.f, -1.f), a); }
-PSB_D float2 add_ib(float2 a, float2 b) { return fma2(make_float2(b.y, b.x), make_float2(-1.f, 1.f), a); }
+PSB_D cpx sub_ib(cpx a, cpx b) { return fma2(c_make(c_im(b), c_re(b)), c_make(1.f, -1.f), a); }
+PSB_D cpx add_ib(cpx a, cpx b) { return fma2(c_make(c_im(b), c_re(b)), c_make(-1.f, 1.f), a); }
 
 // multiply by exp(DIR * 2*pi*i*K/16), constants folded
 template <int K, int DIR>
-PSB_D float2 rot16(float2 a) {
+PSB_D cpx rot16(cpx a) {
     constexpr int k = ((K % 16) + 16) % 16;
     if constexpr (k == 0) return a;
-    else if constexpr (k == 8) return make_float2(-a.x, -a.y);
-    else if constexpr (k == 4) return DIR < 0 ? mul2(make_float2(a.y, a.x), make_float2(1.f, -1.f))     // -i*a
-                                              : mul2(make_float2(a.y, a.x), make_float2(-1.f, 1.f));    // +i*a
-    else if constexpr (k == 12) return DIR < 0 ? mul2(make_float2(a.y, a.x), make_float2(-1.f, 1.f))
-                                               : mul2(make_float2(a.y, a.x), make_float2(1.f, -1.f));
+    else if constexpr (k == 8) return c_make(-c_re(a), -c_im(a));
+    else if constexpr (k == 4) return DIR < 0 ? mul2(c_make(c_im(a), c_re(a)), c_make(1.f, -1.f))     // -i*a
+                                              : mul2(c_make(c_im(a), c_re(a)), c_make(-1.f, 1.f));    // +i*a
+    else if constexpr (k == 12) return DIR < 0 ? mul2(c_make(c_im(a), c_re(a)), c_make(-1.f, 1.f))
+                                               : mul2(c_make(c_im(a), c_re(a)), c_make(1.f, -1.f));
     else {
         constexpr float c = (k == 1 || k == 15) ? kC1 : (k == 2 || k == 14) ? kR2 : (k == 3 || k == 13) ? kS1
                           : (k == 5 || k == 11) ? -kS1 : (k == 6 || k == 10) ? -kR2 : -kC1;
         constexpr float sabs = (k == 1 || k == 7 || k == 9 || k == 15) ? kS1
                              : (k == 2 || k == 6 || k == 10 || k == 14) ? kR2 : kC1;
         constexpr float s = (k < 8 ? sabs : -sabs) * (DIR < 0 ? -1.0f : 1.0f);
-        return cmulp(a, make_float2(c, s));
+        return cmulp(a, c_make(c, s));
     }
 }
 
 template <int DIR>
-PSB_D void radix4(float2& a0, float2& a1, float2& a2, float2& a3) {
-    const float2 s02 = add2(a0, a2), d02 = sub2(a0, a2);
-    const float2 s13 = add2(a1, a3), d13 = sub2(a1, a3);
+PSB_D void radix4(cpx& a0, cpx& a1, cpx& a2, cpx& a3) {
+    const cpx s02 = add2(a0, a2), d02 = sub2(a0, a2);
+    const cpx s13 = add2(a1, a3), d13 = sub2(a1, a3);
     a0 = add2(s02, s13);
     a2 = sub2(s02, s13);
-    const float2 m = sub_ib(d02, d13), q = add_ib(d02, d13);   // forward: X1 = d02 - i*d13, X3 = d02 + i*d13
+    const cpx m = sub_ib(d02, d13), q = add_ib(d02, d13);   // forward: X1 = d02 - i*d13, X3 = d02 + i*d13
     a1 = DIR < 0 ? m : q;
     a3 = DIR < 0 ? q : m;
 }
 
 template <int DIR>
-PSB_D void radix2(float2& a0, float2& a1) {
-    const float2 s = add2(a0, a1), d = sub2(a0, a1);
+PSB_D void radix2(cpx& a0, cpx& a1) {
+    const cpx s = add2(a0, a1), d = sub2(a0, a1);
     a0 = s;
     a1 = d;
 }
 
 // 16-point DFT, natural order in and out (4 x 4 Cooley-Tukey: n = 4*n1 + n2, k = k1 + 4*k2)
 template <int DIR>
-PSB_D void radix16(float2 (&v)[16]) {
-    float2 a[4][4];   // a[n2][k1]
+PSB_D void radix16(cpx (&v)[16]) {
+    cpx a[4][4];   // a[n2][k1]
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) {
-        float2 t0 = v[n2], t1 = v[4 + n2], t2 = v[8 + n2], t3 = v[12 + n2];
+        cpx t0 = v[n2], t1 = v[4 + n2], t2 = v[8 + n2], t3 = v[12 + n2];
         radix4<DIR>(t0, t1, t2, t3);
         a[n2][0] = t0; a[n2][1] = t1; a[n2][2] = t2; a[n2][3] = t3;
     }
@@ -116,7 +138,7 @@ PSB_D void radix16(float2 (&v)[16]) {
     a[3][1] = rot16<3, DIR>(a[3][1]); a[3][2] = rot16<6, DIR>(a[3][2]); a[3][3] = rot16<9, DIR>(a[3][3]);
 #pragma unroll
     for (int k1 = 0; k1 < 4; ++k1) {
-        float2 t0 = a[0][k1], t1 = a[1][k1], t2 = a[2][k1], t3 = a[3][k1];
+        cpx t0 = a[0][k1], t1 = a[1][k1], t2 = a[2][k1], t3 = a[3][k1];
         radix4<DIR>(t0, t1, t2, t3);
         v[k1] = t0; v[k1 + 4] = t1; v[k1 + 8] = t2; v[k1 + 12] = t3;
     }
@@ -127,15 +149,16 @@ PSB_D void radix16(float2 (&v)[16]) {
 // N = 512 (radix 16 x 2 x 16):   w[t-1] = exp(-2*pi*i*j*t/512),  w2 = exp(-2*pi*i*(j & 15)/32)
 template <int N>
 struct Twiddles {
-    float2 w[15];
-    float2 w2;
+    cpx w[15];
+    cpx w2;
     // `staged` is the staged table of Plan<N, 16> built by tables.cu (layout: fft_core.cuh twiddle_offset)
-    PSB_D void load(const float2* PSB_RESTRICT staged, int j) {
+    PSB_D void load(const float2* PSB_RESTRICT staged_f2, int j) {
+        const cpx* PSB_RESTRICT staged = reinterpret_cast<const cpx*>(staged_f2);
         static_assert(N == 256 || N == 512, "fast path line sizes");
         if constexpr (N == 256) {
 #pragma unroll
             for (int t = 1; t < 16; ++t) w[t - 1] = staged[(t - 1) * 16 + j];
-            w2 = make_float2(1.f, 0.f);
+            w2 = c_make(1.f, 0.f);
         } else {
             w2 = staged[j & 15];                                           // stage 2 block: R = 2, NS = 16
 #pragma unroll
@@ -145,17 +168,17 @@ struct Twiddles {
 };
 
 // ---- the line transform -----------------------------------------------------------------------------
-// Xchg policy:  float2* buf(int i)      exchange buffer of the i-th exchange of the current tile
-//               int at(int q)           float2 index of position q of this thread's line in that buffer
+// Xchg policy:  cpx* buf(int i)         exchange buffer of the i-th exchange of the current tile
+//               int at(int q)           element index of position q of this thread's line in that buffer
 //               void after_store(int i) all stores of exchange i visible to the line's threads
 //               void after_load(int i)  all loads of exchange i done (buffer reusable)
 template <int N, int DIR, class Xchg>
-PSB_D void line_fft(float2 (&v)[16], const Twiddles<N>& tw, int j, const Xchg& x, int xi0) {
+PSB_D void line_fft(cpx (&v)[16], const Twiddles<N>& tw, int j, const Xchg& x, int xi0) {
     constexpr int T = N / 16;
     // stage 1: radix 16 over positions j + t*T, outputs to 16*j + u
     radix16<DIR>(v);
     {
-        float2* sm = x.buf(xi0);
+        cpx* sm = x.buf(xi0);
 #pragma unroll
         for (int u = 0; u < 16; ++u) sm[x.at(16 * j + u)] = v[u];
         x.after_store(xi0);
@@ -166,10 +189,10 @@ PSB_D void line_fft(float2 (&v)[16], const Twiddles<N>& tw, int j, const Xchg& x
     if constexpr (N == 512) {
         // stage 2: radix 2, NS = 16: butterfly m pairs v[m], v[m + 8] (positions b, b + 256 with b = j + 32*m),
         // twiddle exp(-+2*pi*i*(b & 15)/32) = w2, outputs to (b/16)*32 + (b & 15) + u*16
-        float2* sm = x.buf(xi0 + 1);
+        cpx* sm = x.buf(xi0 + 1);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            float2 a0 = v[m], a1 = DIR < 0 ? cmulp(v[m + 8], tw.w2) : cmulcp(v[m + 8], tw.w2);
+            cpx a0 = v[m], a1 = DIR < 0 ? cmulp(v[m + 8], tw.w2) : cmulcp(v[m + 8], tw.w2);
             radix2<DIR>(a0, a1);
             const int b = j + 32 * m;
             const int q0 = (b >> 4) * 32 + (b & 15);

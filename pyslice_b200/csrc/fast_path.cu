@@ -29,6 +29,7 @@
 #include <cuda.h>
 
 #include <atomic>
+#include <cstring>
 #include <string>
 
 namespace psb {
@@ -65,6 +66,21 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
+// same, with an L2 eviction-priority hint: the transmission stack streams through L2 once (evict first) while
+// psi must stay resident between the passes
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
 // 2-D tiled tensor copy (TMA): box of the tensor map at element coordinates (c0 = column, c1 = row)
 __device__ __forceinline__ void tensor2d_g2s(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
     asm volatile(
@@ -84,7 +100,15 @@ struct RowPassParams {
     const float2* py;            // [N] propagator factor along the line
     const float2* tw;            // staged twiddle table of Plan<N, 16>
     long long n_units;           // n_img * nx / lines-per-warp
+    // R_TRANSMIT: image = frame*pair_count + ml holds V_{2m} + i*V_{2m+1}, m = pair_begin + ml; the transmission
+    // function of slice s of that frame goes to t_out[(frame*pair_nz + s)*nx*N + ...] (v_out likewise, optional)
+    float2* t_out;
+    float* v_out;
+    float scale, sigma;
+    int pair_count, pair_nz, pair_begin;
 };
+
+enum RowMode { R_STEP = 0, R_TRANSMIT = 1 };
 
 template <int N>
 struct RowCfg {
@@ -99,27 +123,29 @@ struct RowCfg {
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
 };
 
+using fast::cpx;
+
 template <int N>
 struct RowXchg {
-    float2* x;
+    cpx* x;
     int c;
-    __device__ __forceinline__ float2* buf(int) const { return x; }
+    __device__ __forceinline__ cpx* buf(int) const { return x; }
     __device__ __forceinline__ int at(int q) const { return c * RowCfg<N>::NP + q + (q >> 4); }
     __device__ __forceinline__ void after_store(int) const { __syncwarp(); }
     __device__ __forceinline__ void after_load(int) const { __syncwarp(); }
 };
 
-template <int N>
+template <int N, int MODE>
 __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p) {
     using C = RowCfg<N>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* sm = reinterpret_cast<float2*>(smem_raw);
+    cpx* sm = reinterpret_cast<cpx*>(smem_raw);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: bulk copies take uniform operands
     const int lane = threadIdx.x & 31;
-    float2* land_psi = sm + (size_t)warp * C::kWarpElems;
-    float2* land_t = land_psi + C::kLand;
-    float2* xb = land_t + C::kLand;
-    float2* spy = sm + (size_t)C::kWarps * C::kWarpElems;
+    cpx* land_psi = sm + (size_t)warp * C::kWarpElems;
+    cpx* land_t = land_psi + C::kLand;
+    cpx* xb = land_t + C::kLand;
+    cpx* spy = sm + (size_t)C::kWarps * C::kWarpElems;
     uint64_t* bars = reinterpret_cast<uint64_t*>(spy + N) + 2 * warp;
     uint64_t* mb_psi = bars;
     uint64_t* mb_t = bars + 1;
@@ -129,7 +155,8 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
         mbar_init(mb_t, 1);
         mbar_init_fence();
     }
-    for (int i = threadIdx.x; i < N; i += blockDim.x) spy[i] = p.py[i];
+    if constexpr (MODE == R_STEP)
+        for (int i = threadIdx.x; i < N; i += blockDim.x) spy[i] = reinterpret_cast<const cpx*>(p.py)[i];
     __syncthreads();
 
     const int c = lane / C::T, j = lane % C::T;
@@ -137,6 +164,7 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
     tw.load(p.tw, j);
     const RowXchg<N> xc{xb, c};
 
+    const uint64_t stream_once = l2_policy_evict_first();
     const long long GW = (long long)gridDim.x * C::kWarps;
     long long u = (long long)blockIdx.x * C::kWarps + warp;
     const int units_per_img = p.nx / C::LPW;
@@ -146,12 +174,12 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
             mbar_expect_tx(mb_psi, C::kBytes);
             bulk_g2s(land_psi, p.psi + unit * C::kLand, C::kBytes, mb_psi);
         }
-        if (want_t) {
+        if (MODE == R_STEP && want_t) {
             const long long img = unit / units_per_img;
             const long long row0 = (unit % units_per_img) * C::LPW;
             const float2* src = p.t + (img / p.probes) * p.t_frame_stride + row0 * N;
             mbar_expect_tx(mb_t, C::kBytes);
-            bulk_g2s(land_t, src, C::kBytes, mb_t);
+            bulk_g2s_hint(land_t, src, C::kBytes, mb_t, stream_once);
         }
     };
     if (u < p.n_units && lane == 0) issue(u, true, true);
@@ -160,22 +188,51 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
         const uint32_t parity = it & 1u;
         const long long un = u + GW;
         const bool next = un < p.n_units;
-        float2 v[16];
+        cpx v[16];
         mbar_wait(mb_psi, parity);
+        if constexpr (MODE == R_STEP) {
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(land_psi[c * N + j + e * C::T], spy[j + e * C::T]);
+            for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(land_psi[c * N + j + e * C::T], spy[j + e * C::T]);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = land_psi[c * N + j + e * C::T];
+        }
         __syncwarp();
         if (lane == 0 && next) issue(un, true, false);
         fast::line_fft<N, +1>(v, tw, j, xc, 0);
-        mbar_wait(mb_t, parity);
+        if constexpr (MODE == R_STEP) {
+            mbar_wait(mb_t, parity);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], land_t[c * N + j + e * C::T]);
-        __syncwarp();
-        if (lane == 0 && next) issue(un, false, true);
-        fast::line_fft<N, -1>(v, tw, j, xc, 0);
-        float2* dst = p.psi + u * C::kLand + c * N + j;
+            for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], land_t[c * N + j + e * C::T]);
+            __syncwarp();
+            if (lane == 0 && next) issue(un, false, true);
+            fast::line_fft<N, -1>(v, tw, j, xc, 0);
+            cpx* dst = reinterpret_cast<cpx*>(p.psi) + u * C::kLand + c * N + j;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) dst[e * C::T] = v[e];
+            for (int e = 0; e < 16; ++e) dst[e * C::T] = v[e];
+        } else {
+            // potentials.py:336-342 + multislice.py:281-282: V = Re/Im(IFFT2) * scale, t = exp(i*sigma*V), two slices per image
+            const long long img = u / units_per_img;
+            const long long row = (u % units_per_img) * C::LPW + c;
+            const long long fr = img / p.pair_count;
+            const int m = p.pair_begin + (int)(img % p.pair_count);
+            const long long img_elems = (long long)p.nx * N;
+            const long long o = (fr * p.pair_nz + 2 * m) * img_elems + row * N + j;
+            const bool has_b = 2 * m + 1 < p.pair_nz;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                const float va = fast::c_re(v[e]) * p.scale, vb = fast::c_im(v[e]) * p.scale;
+                float sn, cs;
+                sincosf(p.sigma * va, &sn, &cs);
+                p.t_out[o + e * C::T] = make_float2(cs, sn);
+                if (p.v_out) p.v_out[o + e * C::T] = va;
+                if (has_b) {
+                    sincosf(p.sigma * vb, &sn, &cs);
+                    p.t_out[o + img_elems + e * C::T] = make_float2(cs, sn);
+                    if (p.v_out) p.v_out[o + img_elems + e * C::T] = vb;
+                }
+            }
+        }
     }
 }
 
@@ -203,20 +260,21 @@ struct ColCfg {
 // barrier of a tile doubles as the "landing buffer is free" point: thread 0 then issues the next tile's TMA.
 template <int N>
 struct ColXchg {
-    float2* b0;
-    float2* b1;
+    cpx* b0;
+    cpx* b1;
     int c;
     const CUtensorMap* map;
     uint64_t* mb;
-    float2* land;
+    cpx* land;
     int next_c0, next_r0;        // tensor coordinates of the next tile; next_c0 < 0: nothing to prefetch
-    __device__ __forceinline__ float2* buf(int i) const { return (i & 1) ? b1 : b0; }
+    int hook_i;                  // index of the tile's first exchange
+    __device__ __forceinline__ cpx* buf(int i) const { return (i & 1) ? b1 : b0; }
     __device__ __forceinline__ int at(int q) const {
         return (ColCfg<N>::W == 8 ? q + (q >> 4) : q) * ColCfg<N>::W + c;
     }
     __device__ __forceinline__ void after_store(int i) const {
         __syncthreads();
-        if (i == 0 && next_c0 >= 0 && threadIdx.x == 0) {
+        if (i == hook_i && next_c0 >= 0 && threadIdx.x == 0) {      // first barrier of the tile
             mbar_expect_tx(mb, ColCfg<N>::kBytes);
 #pragma unroll
             for (int h = 0; h < N / ColCfg<N>::kBoxRows; ++h)
@@ -226,14 +284,16 @@ struct ColXchg {
     __device__ __forceinline__ void after_load(int) const {}
 };
 
-template <int N, int NY>
+enum ColMode { C_PROPAGATE = 0, C_INVERSE = 1 };
+
+template <int N, int NY, int MODE>
 __global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant__ CUtensorMap tmap, const ColPassParams p) {
     using C = ColCfg<N>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* land = reinterpret_cast<float2*>(smem_raw);
-    float2* xb0 = land + C::kLand;
-    float2* xb1 = xb0 + C::kX;
-    float2* spx = xb1 + C::kX;
+    cpx* land = reinterpret_cast<cpx*>(smem_raw);
+    cpx* xb0 = land + C::kLand;
+    cpx* xb1 = xb0 + C::kX;
+    cpx* spx = xb1 + C::kX;
     uint64_t* mb = reinterpret_cast<uint64_t*>(spx + N);
 
     const int tid = threadIdx.x;
@@ -241,7 +301,8 @@ __global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant
         mbar_init(mb, 1);
         mbar_init_fence();
     }
-    for (int i = tid; i < N; i += 256) spx[i] = p.px[i];
+    if constexpr (MODE == C_PROPAGATE)
+        for (int i = tid; i < N; i += 256) spx[i] = reinterpret_cast<const cpx*>(p.px)[i];
     __syncthreads();
 
     const int c = tid % C::W, j = tid / C::W;
@@ -251,7 +312,7 @@ __global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant
 
     long long tile = blockIdx.x;
     const long long G = gridDim.x;
-    ColXchg<N> xc{xb0, xb1, c, &tmap, mb, land, -1, 0};
+    ColXchg<N> xc{xb0, xb1, c, &tmap, mb, land, -1, 0, 0};
     if (tile < p.n_tiles && tid == 0) {
         mbar_expect_tx(mb, C::kBytes);
 #pragma unroll
@@ -268,15 +329,22 @@ __global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant
             xc.next_c0 = -1;
         }
         mbar_wait(mb, it & 1u);
-        float2 v[16];
+        cpx v[16];
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = land[(j + e * C::T) * C::W + c];
-        fast::line_fft<N, -1>(v, tw, j, xc, 0);
+        if constexpr (MODE == C_PROPAGATE) {
+            fast::line_fft<N, -1>(v, tw, j, xc, 0);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], spx[j + e * C::T]);
-        xc.next_c0 = -1;
-        fast::line_fft<N, +1>(v, tw, j, xc, fast::exchanges<N>());
-        float2* dst = p.psi + (tile / kTilesPerImg) * ((long long)N * NY) + (tile % kTilesPerImg) * C::W + j * NY + c;
+            for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], spx[j + e * C::T]);
+            xc.next_c0 = -1;
+            fast::line_fft<N, +1>(v, tw, j, xc, fast::exchanges<N>());
+        } else {
+            // one transform per tile: alternate the exchange buffer between tiles so a single barrier per
+            // exchange still orders the reuse (N = 512 already alternates inside the transform)
+            xc.hook_i = fast::exchanges<N>() == 1 ? (int)(it & 1u) : 0;
+            fast::line_fft<N, +1>(v, tw, j, xc, xc.hook_i);
+        }
+        cpx* dst = reinterpret_cast<cpx*>(p.psi) + (tile / kTilesPerImg) * ((long long)N * NY) + (tile % kTilesPerImg) * C::W + j * NY + c;
 #pragma unroll
         for (int e = 0; e < 16; ++e) dst[e * C::T * NY] = v[e];
     }
@@ -327,31 +395,31 @@ int encode_cols_map(CUtensorMap* map, float2* psi, long long rows_total, int ny,
     return PSB_OK;
 }
 
-template <int N>
+template <int N, int MODE>
 int rows_go(const RowPassParams& p, cudaStream_t s) {
     using C = RowCfg<N>;
     static bool ready = false;
     if (!ready) {
-        int rc = ensure_smem(fast_rows_kernel<N>, C::kSmem, "fast row pass");
+        int rc = ensure_smem(fast_rows_kernel<N, MODE>, C::kSmem, "fast row pass");
         if (rc != PSB_OK) return rc;
         ready = true;
     }
     long long want = (p.n_units + C::kWarps - 1) / C::kWarps;
     const int sms = rt::sm_count();
     const int grid = (int)(want < sms ? want : sms);
-    fast_rows_kernel<N><<<grid, 512, C::kSmem, s>>>(p);
+    fast_rows_kernel<N, MODE><<<grid, 512, C::kSmem, s>>>(p);
     ++launch_counter();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast row pass launch: ") + cudaGetErrorString(e));
     return PSB_OK;
 }
 
-template <int N, int NY>
+template <int N, int NY, int MODE>
 int cols_go(float2* psi, int n_img, const float2* px, const float2* tw, cudaStream_t s) {
     using C = ColCfg<N>;
     static bool ready = false;
     if (!ready) {
-        int rc = ensure_smem(fast_cols_kernel<N, NY>, C::kSmem, "fast column pass");
+        int rc = ensure_smem(fast_cols_kernel<N, NY, MODE>, C::kSmem, "fast column pass");
         if (rc != PSB_OK) return rc;
         ready = true;
     }
@@ -370,7 +438,7 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* tw, cudaStre
     p.n_tiles = (long long)n_img * (NY / C::W);
     const long long slots = 2LL * rt::sm_count();
     const int grid = (int)(p.n_tiles < slots ? p.n_tiles : slots);
-    fast_cols_kernel<N, NY><<<grid, 256, C::kSmem, s>>>(map, p);
+    fast_cols_kernel<N, NY, MODE><<<grid, 256, C::kSmem, s>>>(map, p);
     ++launch_counter();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast column pass launch: ") + cudaGetErrorString(e));
@@ -380,6 +448,7 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* tw, cudaStre
 }  // namespace
 
 void fast_path_enable(int on) { g_fast_enabled.store(on ? 1 : 0); }
+bool fast_path_enabled() { return g_fast_enabled.load() != 0; }
 
 bool fast_slice_supported(int nx, int ny) {
     if (!g_fast_enabled.load()) return false;
@@ -389,26 +458,53 @@ bool fast_slice_supported(int nx, int ny) {
 int launch_fast_rows(float2* psi, int n_img, int nx, int ny, const float2* t_slice, long long t_frame_stride,
                      int probes, const float2* py, cudaStream_t s) {
     RowPassParams p;
+    std::memset(&p, 0, sizeof(p));
     p.psi = psi; p.t = t_slice; p.t_frame_stride = t_frame_stride; p.probes = probes; p.nx = nx; p.py = py;
     int rc = twiddles_for(ny, &p.tw, s);
     if (rc != PSB_OK) return rc;
     if (ny == 256) {
         p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
-        return rows_go<256>(p, s);
+        return rows_go<256, R_STEP>(p, s);
     }
     p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
-    return rows_go<512>(p, s);
+    return rows_go<512, R_STEP>(p, s);
 }
 
-int launch_fast_cols(float2* psi, int n_img, int nx, int ny, const float2* px, cudaStream_t s) {
+int launch_fast_rows_transmit(float2* pairs, int n_img, int nx, int ny, float scale, float sigma, float2* t_out,
+                              float* v_out, int pair_count, int pair_nz, int pair_begin, cudaStream_t s) {
+    RowPassParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = pairs; p.nx = nx; p.probes = 1;
+    p.t_out = t_out; p.v_out = v_out; p.scale = scale; p.sigma = sigma;
+    p.pair_count = pair_count; p.pair_nz = pair_nz; p.pair_begin = pair_begin;
+    int rc = twiddles_for(ny, &p.tw, s);
+    if (rc != PSB_OK) return rc;
+    if (ny == 256) {
+        p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
+        return rows_go<256, R_TRANSMIT>(p, s);
+    }
+    p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
+    return rows_go<512, R_TRANSMIT>(p, s);
+}
+
+template <int MODE>
+static int cols_dispatch(float2* psi, int n_img, int nx, int ny, const float2* px, cudaStream_t s) {
     const float2* tw = nullptr;
     int rc = twiddles_for(nx, &tw, s);
     if (rc != PSB_OK) return rc;
-    if (nx == 256 && ny == 256) return cols_go<256, 256>(psi, n_img, px, tw, s);
-    if (nx == 256 && ny == 512) return cols_go<256, 512>(psi, n_img, px, tw, s);
-    if (nx == 512 && ny == 256) return cols_go<512, 256>(psi, n_img, px, tw, s);
-    if (nx == 512 && ny == 512) return cols_go<512, 512>(psi, n_img, px, tw, s);
+    if (nx == 256 && ny == 256) return cols_go<256, 256, MODE>(psi, n_img, px, tw, s);
+    if (nx == 256 && ny == 512) return cols_go<256, 512, MODE>(psi, n_img, px, tw, s);
+    if (nx == 512 && ny == 256) return cols_go<512, 256, MODE>(psi, n_img, px, tw, s);
+    if (nx == 512 && ny == 512) return cols_go<512, 512, MODE>(psi, n_img, px, tw, s);
     return fail(PSB_ERR_UNSUPPORTED, "fast column pass: unsupported grid");
+}
+
+int launch_fast_cols(float2* psi, int n_img, int nx, int ny, const float2* px, cudaStream_t s) {
+    return cols_dispatch<C_PROPAGATE>(psi, n_img, nx, ny, px, s);
+}
+
+int launch_fast_cols_inverse(float2* imgs, int n_img, int nx, int ny, cudaStream_t s) {
+    return cols_dispatch<C_INVERSE>(imgs, n_img, nx, ny, nullptr, s);
 }
 
 }  // namespace psb

@@ -7,6 +7,7 @@ namespace psb {
 // true when both passes of a slice step have a fused kernel for this grid (and the fast path is enabled)
 bool fast_slice_supported(int nx, int ny);
 void fast_path_enable(int on);
+bool fast_path_enabled();
 
 // psi[x, ky] -> FFT_y( t[x, y] * IFFT_y( py[ky] * psi[x, ky] ) ) in place over n_img contiguous (nx, ny) images;
 // image i uses the transmission slice t_slice + (i / probes) * t_frame_stride.
@@ -14,5 +15,17 @@ int launch_fast_rows(float2* psi, int n_img, int nx, int ny, const float2* t_sli
                      int probes, const float2* py, cudaStream_t s);
 // psi[x, ky] -> IFFT_x( px[kx] * FFT_x( psi[x, ky] ) ) in place (unnormalised; px carries the 1/(nx*ny)).
 int launch_fast_cols(float2* psi, int n_img, int nx, int ny, const float2* px, cudaStream_t s);
+
+// potential build (potentials.py:336-342): in-place inverse column transform of n_img slice-pair spectra, then
+// inverse row transform with the transmission epilogue t = exp(i*sigma*scale*Re/Im(.)) for the two slices of a pair
+int launch_fast_cols_inverse(float2* imgs, int n_img, int nx, int ny, cudaStream_t s);
+int launch_fast_rows_transmit(float2* pairs, int n_img, int nx, int ny, float scale, float sigma, float2* t_out,
+                              float* v_out, int pair_count, int pair_nz, int pair_begin, cudaStream_t s);
+
+// structure-factor sum of slice pairs [pair_begin, pair_begin + pair_count) of nf frames into out (nf, pair_count, nx, ny)
+// (sf_fast.cu: precomputed phase tables + TMA-fed packed-FMA tiles); any grid size
+int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
+                   int ny, int pair_begin, int pair_count, int nf, const float* ff, float2* out, cudaStream_t s);
+void sf_fast_release();
 
 }  // namespace psb

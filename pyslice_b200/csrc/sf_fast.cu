@@ -1,0 +1,392 @@
+// Structure-factor sum of the projected potential, pipelined version (reference: src/multislice/potentials.py
+// :319-330, the einsum over exp(-2 pi i kx x) exp(-2 pi i ky y) of the atoms of a slice, times the form factor).
+//
+// Same arithmetic as StructureFactorPaired (potential_kernels.cuh: quarter spectrum, four real sums per slot,
+// two slices packed per complex image, Nyquist lines riding in slot 0), restructured so the hot loop is nothing
+// but shared-memory loads and packed FMAs:
+//
+//   K1  PhaseTables   once per chunk: (cos, sin)(2 pi g u) of every atom entry of the chunk for every
+//                     non-negative frequency slot g of both axes, with the exact 32-bit fixed-point phase
+//                     reduction, laid out [tile][entry][slot-in-tile] so that the rows a tile needs for one
+//                     (slice, type) segment are ONE contiguous block;
+//   K2  SfTiles       one CTA per (64 x 32 slot tile, slice pair, frame): the blocks of up to 32 atoms stream
+//                     global -> shared with cp.async.bulk through a 2-stage mbarrier ring while the previous
+//                     block is accumulated with FFMA2 (a thread owns 4 x 2 slots x 4 sums = 16 packed
+//                     accumulators); form factor, pairing and the mirror expansion as before.
+//
+// The tables stay L2-resident between K1 and K2 (a few MB per chunk).
+#include "fast_fft.cuh"
+#include "fast_path.h"
+#include "potential_kernels.cuh"
+#include "psb_rt.h"
+
+#include <cstring>
+#include <mutex>
+#include <string>
+
+namespace psb {
+
+namespace {
+
+using fast::cpx;
+
+constexpr int TX = 64, TY = 32, CH = 32;      // slots per tile along kx / ky, atoms per staged block
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        " .reg .pred p;\n"
+        "WAIT_%=:\n"
+        " mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        " @p bra DONE_%=;\n"
+        " bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(b)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct SfFastParams {
+    const int* offsets;         // (nf, nseg+1), first frame of the chunk
+    const unsigned int* ux;     // (nf, cap)
+    const unsigned int* uy;
+    int cap, nz, ntypes, nx, ny;
+    int pair_begin, pair_count;
+    int tiles_x, tiles_y;
+    float2* tabx;               // [nf][tiles_x][cap][TX]   (cos, sin)(2 pi g u); slot 0 of an even axis: (1, cos(pi n u))
+    float2* taby;               // [nf][tiles_y][cap][TY]
+    float* snx;                 // [nf][cap]  Nyquist sine (corner term), even axes only
+    float* sny;
+    const float* ff;            // (ntypes, nx, ny)
+    float2* out;                // (nf, pair_count, nx, ny)
+};
+
+// (cos, sin) of 2*pi*g*u for one axis entry, exactly as StructureFactorPaired stages it
+__device__ __forceinline__ float2 slot_phase(int g, unsigned int u, int n, bool nyq, float* sn_out) {
+    float2 z = unit_phase(g, u);          // (cos, -sin)
+    z.y = -z.y;
+    if (g == 0 && nyq) {
+        const float2 q = unit_phase(n / 2, u);
+        z.y = q.x;
+        *sn_out = q.y;
+    }
+    return z;
+}
+
+// K1: one warp per atom entry of the chunk
+__global__ void __launch_bounds__(256) phase_tables_kernel(const SfFastParams p) {
+    const int fl = blockIdx.y;
+    const int nseg = p.nz * p.ntypes;
+    const int* off = p.offsets + (long long)fl * (nseg + 1);
+    const int s_begin = 2 * p.pair_begin;
+    int s_end = 2 * (p.pair_begin + p.pair_count);
+    if (s_end > p.nz) s_end = p.nz;
+    const int e_begin = off[s_begin * p.ntypes], e_end = off[s_end * p.ntypes];
+    const int e = e_begin + blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (e >= e_end) return;
+    const int lane = threadIdx.x & 31;
+    const unsigned int ux = p.ux[(long long)fl * p.cap + e], uy = p.uy[(long long)fl * p.cap + e];
+    const int nsx = StructureFactorPaired::slots(p.nx), nsy = StructureFactorPaired::slots(p.ny);
+    const bool nqx = p.nx % 2 == 0, nqy = p.ny % 2 == 0;
+    float sn = 0.f;
+    for (int g = lane; g < p.tiles_x * TX; g += 32) {
+        float2 z = g < nsx ? slot_phase(g, ux, p.nx, nqx, &sn) : make_float2(0.f, 0.f);
+        p.tabx[(((long long)fl * p.tiles_x + g / TX) * p.cap + e) * TX + g % TX] = z;
+    }
+    if (lane == 0 && nqx) p.snx[(long long)fl * p.cap + e] = sn;
+    for (int g = lane; g < p.tiles_y * TY; g += 32) {
+        float2 z = g < nsy ? slot_phase(g, uy, p.ny, nqy, &sn) : make_float2(0.f, 0.f);
+        p.taby[(((long long)fl * p.tiles_y + g / TY) * p.cap + e) * TY + g % TY] = z;
+    }
+    if (lane == 0 && nqy) p.sny[(long long)fl * p.cap + e] = sn;
+}
+
+// iterator over the staged blocks of one slice pair, in the order (slice of the pair, type, block)
+struct BlockIter {
+    int h, t, c0, e;            // current slice-of-pair, type, block start, segment end
+    bool valid;
+};
+
+__device__ __forceinline__ void iter_seek(BlockIter& it, const int* off, int m, int nz, int ntypes) {
+    // position on the first non-empty segment at or after (it.h, it.t); c0 = its start
+    while (it.h < 2) {
+        const int s = 2 * m + it.h;
+        if (s < nz) {
+            while (it.t < ntypes) {
+                const int b = off[s * ntypes + it.t], e = off[s * ntypes + it.t + 1];
+                if (b < e) {
+                    it.c0 = b;
+                    it.e = e;
+                    it.valid = true;
+                    return;
+                }
+                ++it.t;
+            }
+        }
+        ++it.h;
+        it.t = 0;
+    }
+    it.valid = false;
+}
+__device__ __forceinline__ void iter_next(BlockIter& it, const int* off, int m, int nz, int ntypes) {
+    it.c0 += CH;
+    if (it.c0 < it.e) return;
+    ++it.t;
+    iter_seek(it, off, m, nz, ntypes);
+}
+
+constexpr int kStageElems = CH * (TX + TY);
+constexpr size_t kSfSmem = 2 * (size_t)kStageElems * sizeof(float2) + 32 * 256 * sizeof(float) + 2 * sizeof(uint64_t);
+
+// K2
+__global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    cpx* stage = reinterpret_cast<cpx*>(smem_raw);                         // [2][CH*TX + CH*TY]
+    float* stash = reinterpret_cast<float*>(stage + 2 * kStageElems);      // [32][256]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stash + 32 * 256);        // [2]
+
+    const int nsx = StructureFactorPaired::slots(p.nx), nsy = StructureFactorPaired::slots(p.ny);
+    const int tile_x = blockIdx.x / p.tiles_y, tile_y = blockIdx.x % p.tiles_y;
+    const int kx0 = tile_x * TX, ky0 = tile_y * TY;
+    const int ml = blockIdx.y, m = p.pair_begin + ml, fl = blockIdx.z;
+    const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
+    const int nseg = p.nz * p.ntypes;
+    const int* off = p.offsets + (long long)fl * (nseg + 1);
+    const bool nq_x = p.nx % 2 == 0, nq_y = p.ny % 2 == 0;
+    const bool corner_tile = kx0 == 0 && ky0 == 0 && nq_x && nq_y;
+    const float2* tabx = p.tabx + ((long long)fl * p.tiles_x + tile_x) * p.cap * TX;
+    const float2* taby = p.taby + ((long long)fl * p.tiles_y + tile_y) * p.cap * TY;
+    const float* snx = p.snx + (long long)fl * p.cap;
+    const float* sny = p.sny + (long long)fl * p.cap;
+
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int gx[4], gy[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gx[i] = kx0 + ty + 16 * i;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) gy[k] = ky0 + tx + 16 * k;
+
+    // producer side: thread 0 keeps two blocks in flight
+    BlockIter ahead{0, 0, 0, 0, false};
+    iter_seek(ahead, off, m, p.nz, p.ntypes);
+    int issued = 0;
+    auto issue = [&]() {
+        if (!ahead.valid) return;
+        if (tid == 0) {
+            const int nc = ahead.e - ahead.c0 < CH ? ahead.e - ahead.c0 : CH;
+            cpx* dst = stage + (issued & 1) * kStageElems;
+            uint64_t* bar = &full[issued & 1];
+            mbar_expect_tx(bar, (uint32_t)(nc * (TX + TY) * sizeof(float2)));
+            bulk_g2s(dst, tabx + (long long)ahead.c0 * TX, (uint32_t)(nc * TX * sizeof(float2)), bar);
+            bulk_g2s(dst + CH * TX, taby + (long long)ahead.c0 * TY, (uint32_t)(nc * TY * sizeof(float2)), bar);
+        }
+        ++issued;
+        iter_next(ahead, off, m, p.nz, p.ntypes);
+    };
+    issue();
+    issue();
+
+    int used = 0;
+    float tot[4][2][4];     // [i][k][cc, ss, cs, sc], multiplied by the form factor
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) tot[i][k][q] = 0.f;
+        const int s = 2 * m + h;
+        if (s < p.nz) {
+            for (int t = 0; t < p.ntypes; ++t) {
+                const int b = off[s * p.ntypes + t], e = off[s * p.ntypes + t + 1];
+                if (b == e) continue;
+                cpx P[4][2], Q[4][2];      // P = (cc, cs), Q = (sc, ss)
+                float corr = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        P[i][k] = fast::c_make(0.f, 0.f);
+                        Q[i][k] = fast::c_make(0.f, 0.f);
+                    }
+                for (int c0 = b; c0 < e; c0 += CH) {
+                    const int nc = e - c0 < CH ? e - c0 : CH;
+                    const cpx* ex = stage + (used & 1) * kStageElems;
+                    const cpx* ey = ex + CH * TX;
+                    mbar_wait(&full[used & 1], (uint32_t)((used >> 1) & 1));
+#pragma unroll 4
+                    for (int a = 0; a < nc; ++a) {
+                        cpx ys[2];
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) ys[k] = ey[a * TY + tx + 16 * k];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const cpx x = ex[a * TX + ty + 16 * i];
+                            const cpx xc = fast::c_make(fast::c_re(x), fast::c_re(x));
+                            const cpx xs = fast::c_make(fast::c_im(x), fast::c_im(x));
+#pragma unroll
+                            for (int k = 0; k < 2; ++k) {
+                                P[i][k] = fast::fma2(xc, ys[k], P[i][k]);
+                                Q[i][k] = fast::fma2(xs, ys[k], Q[i][k]);
+                            }
+                        }
+                    }
+                    if (corner_tile)
+                        for (int a = 0; a < nc; ++a) corr += __ldg(&snx[c0 + a]) * __ldg(&sny[c0 + a]);
+                    __syncthreads();             // every thread is done with this stage
+                    ++used;
+                    issue();                     // refill it with the block after the one already in flight
+                }
+                const float* ff = p.ff + (long long)t * p.nx * p.ny;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        if (gx[i] < nsx && gy[k] < nsy) {
+                            const int fx0 = gx[i], fx1 = (gx[i] == 0 && nq_x) ? p.nx / 2 : gx[i];
+                            const int fy0 = gy[k], fy1 = (gy[k] == 0 && nq_y) ? p.ny / 2 : gy[k];
+                            const float cc = fast::c_re(P[i][k]), cs = fast::c_im(P[i][k]);
+                            const float sc = fast::c_re(Q[i][k]);
+                            float ss = fast::c_im(Q[i][k]);
+                            if (corner_tile && gx[i] == 0 && gy[k] == 0) ss -= corr;
+                            tot[i][k][0] += cc * __ldg(&ff[(long long)fx0 * p.ny + fy0]);
+                            tot[i][k][1] += ss * __ldg(&ff[(long long)fx1 * p.ny + fy1]);
+                            tot[i][k][2] += cs * __ldg(&ff[(long long)fx0 * p.ny + fy1]);
+                            tot[i][k][3] += sc * __ldg(&ff[(long long)fx1 * p.ny + fy0]);
+                        }
+                    }
+            }
+        }
+        if (h == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) stash[((i * 2 + k) * 4 + q) * 256 + tid] = tot[i][k][q];
+        }
+    }
+    // tot = second slice (B), stash = first slice (A):  Z = S'_A + i*S'_B at up to four mirror positions
+    float2* out = p.out + ((long long)fl * p.pair_count + ml) * p.nx * p.ny;
+    auto emit = [&](int kx, int ky, float ar, float ai, float br, float bi) {
+        out[(long long)kx * p.ny + ky] = make_float2(ar - bi, ai + br);
+    };
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int x = gx[i], y = gy[k];
+            if (x >= nsx || y >= nsy) continue;
+            float A[4], B[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                A[q] = stash[((i * 2 + k) * 4 + q) * 256 + tid];
+                B[q] = tot[i][k][q];
+            }
+            const float acc_ = A[0], ass = A[1], acs = A[2], asc = A[3];
+            const float bcc = B[0], bss = B[1], bcs = B[2], bsc = B[3];
+            if (x > 0 && y > 0) {
+                emit(x, y, acc_ - ass, -(acs + asc), bcc - bss, -(bcs + bsc));
+                emit(p.nx - x, y, acc_ + ass, -(acs - asc), bcc + bss, -(bcs - bsc));
+                emit(x, p.ny - y, acc_ + ass, acs - asc, bcc + bss, bcs - bsc);
+                emit(p.nx - x, p.ny - y, acc_ - ass, acs + asc, bcc - bss, bcs + bsc);
+            } else if (x == 0 && y > 0) {
+                emit(0, y, acc_, -acs, bcc, -bcs);
+                emit(0, p.ny - y, acc_, acs, bcc, bcs);
+                if (nq_x) {
+                    emit(p.nx / 2, y, asc, -ass, bsc, -bss);
+                    emit(p.nx / 2, p.ny - y, asc, ass, bsc, bss);
+                }
+            } else if (x > 0 && y == 0) {
+                emit(x, 0, acc_, -asc, bcc, -bsc);
+                emit(p.nx - x, 0, acc_, asc, bcc, bsc);
+                if (nq_y) {
+                    emit(x, p.ny / 2, acs, -ass, bcs, -bss);
+                    emit(p.nx - x, p.ny / 2, acs, ass, bcs, bss);
+                }
+            } else {
+                emit(0, 0, acc_, 0.f, bcc, 0.f);
+                if (nq_y) emit(0, p.ny / 2, acs, 0.f, bcs, 0.f);
+                if (nq_x) emit(p.nx / 2, 0, asc, 0.f, bsc, 0.f);
+                if (nq_x && nq_y) emit(p.nx / 2, p.ny / 2, ass, 0.f, bss, 0.f);
+            }
+        }
+}
+
+// grow-only workspace for the phase tables, one per process (one process per GPU)
+std::mutex g_ws_mu;
+void* g_ws = nullptr;
+size_t g_ws_bytes = 0;
+
+}  // namespace
+
+void sf_fast_release() {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    rt::dev_free(g_ws);
+    g_ws = nullptr;
+    g_ws_bytes = 0;
+}
+
+int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
+                   int ny, int pair_begin, int pair_count, int nf, const float* ff, float2* out, cudaStream_t s) {
+    SfFastParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.offsets = offsets; p.ux = ux; p.uy = uy; p.cap = cap; p.nz = nz; p.ntypes = ntypes; p.nx = nx; p.ny = ny;
+    p.pair_begin = pair_begin; p.pair_count = pair_count; p.ff = ff; p.out = out;
+    p.tiles_x = (StructureFactorPaired::slots(nx) + TX - 1) / TX;
+    p.tiles_y = (StructureFactorPaired::slots(ny) + TY - 1) / TY;
+    const size_t nx_elems = (size_t)nf * p.tiles_x * cap * TX, ny_elems = (size_t)nf * p.tiles_y * cap * TY;
+    const size_t sn_elems = (size_t)nf * cap;
+    const size_t need = (nx_elems + ny_elems) * sizeof(float2) + 2 * sn_elems * sizeof(float) + 256;
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        if (need > g_ws_bytes) {
+            cudaError_t e = cudaStreamSynchronize(s);      // kernels of earlier chunks may still read the old block
+            if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf workspace sync: ") + cudaGetErrorString(e));
+            rt::dev_free(g_ws);
+            g_ws = rt::dev_alloc(need);
+            g_ws_bytes = g_ws ? need : 0;
+            if (!g_ws) return PSB_ERR_NOMEM;
+        }
+        p.tabx = reinterpret_cast<float2*>(g_ws);
+        p.taby = p.tabx + nx_elems;
+        p.snx = reinterpret_cast<float*>(p.taby + ny_elems);
+        p.sny = p.snx + sn_elems;
+    }
+    static bool ready = false;
+    if (!ready) {
+        cudaError_t e = cudaFuncSetAttribute(sf_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSfSmem);
+        if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf tiles: ") + cudaGetErrorString(e));
+        ready = true;
+    }
+    if (cap > 0) {
+        phase_tables_kernel<<<dim3((cap + 7) / 8, nf), 256, 0, s>>>(p);
+        ++launch_counter();
+    }
+    sf_tiles_kernel<<<dim3(p.tiles_x * p.tiles_y, pair_count, nf), 256, kSfSmem, s>>>(p);
+    ++launch_counter();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf fast launch: ") + cudaGetErrorString(e));
+    return PSB_OK;
+}
+
+}  // namespace psb

@@ -15,10 +15,12 @@ import torch
 from . import _lib, hostmath
 
 # Target size of the wave-function batch that is pushed through all slices at once.  Sized to stay
-# resident in B200's 126 MB L2 across the two passes of a slice step (DESIGN.md "L2 residency").
-PSI_BATCH_BYTES = 48 << 20
+# resident in B200's 126 MB L2 across the two passes of a slice step (DESIGN.md "L2 residency"): the
+# transmission stack streams through L2 with an evict-first hint, so ~3/5 of L2 can hold psi
+# (measured: 148 images of 256^2 = 74 MB still resident, 185 = 93 MB not; profiles/r1e notes).
+PSI_BATCH_BYTES = 80 << 20
 # Upper bound for the transmission-function buffer of one frame batch.
-T_BATCH_BYTES = 24 << 30
+T_BATCH_BYTES = 48 << 30
 # Workspace of the potential build (slice-paired spectra): chunks of this size flow through the three
 # potential kernels while staying L2-resident.
 SCRATCH_BYTES = 32 << 20

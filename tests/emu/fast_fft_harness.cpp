@@ -13,10 +13,10 @@ using namespace psb;
 
 namespace {
 struct HostXchg {
-    float2* a;
-    float2* b;
+    fast::cpx* a;
+    fast::cpx* b;
     std::barrier<>* bar;
-    float2* buf(int i) const { return (i & 1) ? b : a; }
+    fast::cpx* buf(int i) const { return (i & 1) ? b : a; }
     int at(int q) const { return q; }
     void after_store(int) const { bar->arrive_and_wait(); }
     void after_load(int) const {}          // alternating buffers: the next exchange's barrier orders the reuse
@@ -52,7 +52,7 @@ void run_line(const float2* in, float2* out, int reps) {
         th.emplace_back([&, j] {
             fast::Twiddles<N> tw;
             tw.load(table.data(), j);
-            float2 v[16];
+            fast::cpx v[16];
             for (int e = 0; e < 16; ++e) v[e] = in[j + e * T];
             HostXchg x{xa.data(), xb.data(), &bar};
             for (int r = 0; r < reps; ++r) fast::line_fft<N, DIR>(v, tw, j, x, r * fast::exchanges<N>());

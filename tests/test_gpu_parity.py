@@ -315,6 +315,36 @@ def test_fused_slice_step_vs_generic_and_oracle(box, n_probes, aperture, grid):
             assert rel_l2(out[True][p, f], ref[p, f]) < 1e-4
 
 
+@pytest.mark.parametrize("box,n_atoms,types", [
+    ((25.55, 25.55, 9.3), 900, (6, 14, 31)),      # 256 x 256: pipelined structure factor + fused inverse transforms
+    ((51.15, 25.55, 3.2), 500, (14,)),            # 512 x 256
+    ((6.35, 6.35, 4.1), 200, (6, 14, 31)),        # 64 x 64: pipelined structure factor + generic transforms
+    ((4.75, 3.95, 3.2), 150, (5, 7)),             # 48 x 40 (odd half sizes, Bluestein transforms)
+    ((2.45, 2.45, 30.2), 2500, (14,)),            # 25 x 25 odd grid, ~40 atoms per slice and > 32 in many (multi-block segments)
+])
+def test_potential_pipelined_vs_generic_and_oracle(box, n_atoms, types):
+    """psb_build_transmission through the pipelined structure-factor kernels (sf_fast.cu) and the fused
+    inverse transforms against the generic kernels (same inputs) and the oracle's potential."""
+    from pyslice_b200 import engine, hostmath, synthetic
+    traj = synthetic.random_trajectory(n_atoms=n_atoms, box=box, n_frames=3, seed=13, types=types, stray=True)
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    pos = dev(traj.positions)
+    out = {}
+    for fast in (True, False):
+        engine.set_fast_path(fast)
+        try:
+            t, V = engine.build_transmission(plan, pos, want_potential=True)
+            out[fast] = (t.cpu().numpy(), V.cpu().numpy())
+        finally:
+            engine.set_fast_path(True)
+    assert rel_l2(out[True][1], out[False][1]) < 2e-6
+    assert rel_l2(out[True][0], out[False][0]) < 2e-6
+    Vref = orc.potential(xs, ys, zs, traj.positions[1], traj.atom_types)      # (nx, ny, nz)
+    assert rel_l2(np.moveaxis(out[True][1][1], 0, 2), Vref) < 1e-5
+    assert np.allclose(np.abs(out[True][0]), 1.0, atol=1e-6)
+
+
 def test_fused_slice_step_many_images_ragged():
     """image counts that do not divide the persistent grids (148 SMs x 16 warps / x 2 CTAs): 7 frames x 3 probes
     at 256 x 256, every (probe, frame) equal to the generic path within round-off"""
