@@ -52,7 +52,8 @@ void psb_set_fast_path(int enable);
  * Outputs: offsets (F, nz*ntypes+1) exclusive segment offsets (segment = slice*ntypes + type);
  *          atom_list / ux / uy (F, 2*A): atom index and frac(x/Lx), frac(y/Ly) as 32-bit fixed point,
  *          grouped by segment, ascending atom index inside a segment (deterministic).
- * seg_scratch: (F, A, 2) int32 workspace.  lx_eff = nx*dx, ly_eff = ny*dy. */
+ * seg_scratch: int32 workspace of F*(4*A + nz*ntypes) elements (segment ids, unsorted lists, fill cursors).
+ * lx_eff = nx*dx, ly_eff = ny*dy. */
 int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames, int n_atoms, int ntypes,
                   int nz, const double* lo, const double* hi, double dz, double lx_eff, double ly_eff,
                   int32_t* seg_scratch, int32_t* offsets, int32_t* atom_list, uint32_t* ux, uint32_t* uy,

@@ -92,13 +92,21 @@ int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames
     p.lo = lo; p.hi = hi; p.inv_dz = 1.0 / dz; p.inv_lx = 1.0 / lx_eff; p.inv_ly = 1.0 / ly_eff;
     p.seg_of = seg_scratch; p.offsets = offsets; p.atom_list = atom_list; p.ux = ux; p.uy = uy;
     p.cap = 2 * n_atoms;
+    p.unsorted = seg_scratch + (long long)n_frames * n_atoms * 2;
+    p.cursor = p.unsorted + (long long)n_frames * p.cap;
+    rc = rt::zero(p.cursor, (size_t)n_frames * nseg * sizeof(int), s);
+    if (rc != PSB_OK) return rc;
     if (n_atoms > 0) {
         rc = go<BinAssign>(dim3((n_atoms + 255) / 256, n_frames), 0, s, p, "bin_assign");
         if (rc != PSB_OK) return rc;
     }
     rc = go<BinScan>(dim3(n_frames), BinScan::kThreads * sizeof(int), s, p, "bin_scan");
     if (rc != PSB_OK) return rc;
-    if (n_atoms > 0) rc = go<BinCompact>(dim3(nseg, n_frames), BinCompact::kThreads * sizeof(int), s, p, "bin_compact");
+    if (n_atoms > 0) {
+        rc = go<BinScatter>(dim3((n_atoms + 255) / 256, n_frames), 0, s, p, "bin_scatter");
+        if (rc != PSB_OK) return rc;
+        rc = go<BinOrder>(dim3((nseg + 7) / 8, n_frames), 0, s, p, "bin_order");
+    }
     return rc;
 }
 

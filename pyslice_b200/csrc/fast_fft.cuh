@@ -172,8 +172,15 @@ struct Twiddles {
 //               int at(int q)           element index of position q of this thread's line in that buffer
 //               void after_store(int i) all stores of exchange i visible to the line's threads
 //               void after_load(int i)  all loads of exchange i done (buffer reusable)
-template <int N, int DIR, class Xchg>
-PSB_D void line_fft(cpx (&v)[16], const Twiddles<N>& tw, int j, const Xchg& x, int xi0) {
+// `hook()` runs right after the first exchange's stores are visible: by then every thread of the line's
+// sync scope has CONSUMED the values it held on entry (the stores depend on them), which is the earliest
+// point at which the buffer those values were loaded from may be handed back to the async proxy.
+struct NoHook {
+    PSB_D void operator()() const {}
+};
+
+template <int N, int DIR, class Xchg, class Hook = NoHook>
+PSB_D void line_fft(cpx (&v)[16], const Twiddles<N>& tw, int j, const Xchg& x, int xi0, const Hook& hook = Hook()) {
     constexpr int T = N / 16;
     // stage 1: radix 16 over positions j + t*T, outputs to 16*j + u
     radix16<DIR>(v);
@@ -182,6 +189,7 @@ PSB_D void line_fft(cpx (&v)[16], const Twiddles<N>& tw, int j, const Xchg& x, i
 #pragma unroll
         for (int u = 0; u < 16; ++u) sm[x.at(16 * j + u)] = v[u];
         x.after_store(xi0);
+        hook();
 #pragma unroll
         for (int e = 0; e < 16; ++e) v[e] = sm[x.at(j + e * T)];
         x.after_load(xi0);

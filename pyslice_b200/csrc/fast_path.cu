@@ -38,6 +38,8 @@ namespace {
 
 std::atomic<int> g_fast_enabled{1};
 
+using fast::cpx;
+
 // ---- async-proxy plumbing (PTX) --------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -90,6 +92,45 @@ __device__ __forceinline__ void tensor2d_g2s(void* dst, const CUtensorMap* map, 
         : "memory");
 }
 
+// exp(i*x) for the two halves of a packed pair at once (the transmission epilogue: two slices share one pixel of
+// the paired inverse transform).  Cody-Waite reduction by pi/2 in two steps and the degree-7 / degree-8 minimax
+// polynomials on [-pi/4, pi/4], evaluated with packed FMAs; measured max abs error 8.3e-8 for |x| <= 40 against
+// float64 (tools/diag notes in DESIGN.md).  |x| >= 256 takes libdevice's sincosf (never seen: x = sigma*V ~ a few rad).
+__device__ __forceinline__ void pair_cis(cpx x, cpx& ea, cpx& eb) {
+    const float xa = fast::c_re(x), xb = fast::c_im(x);
+    if (fabsf(xa) >= 256.f || fabsf(xb) >= 256.f) {
+        float s, c;
+        sincosf(xa, &s, &c);
+        ea = fast::c_make(c, s);
+        sincosf(xb, &s, &c);
+        eb = fast::c_make(c, s);
+        return;
+    }
+    const float ka = rintf(xa * 0.63661977236758134f), kb = rintf(xb * 0.63661977236758134f);
+    const cpx k = fast::c_make(ka, kb);
+    cpx r = fast::fma2(k, fast::c_make(-1.5707963705062866f, -1.5707963705062866f), x);
+    r = fast::fma2(k, fast::c_make(4.371139000186241e-8f, 4.371139000186241e-8f), r);
+    const cpx s2 = fast::mul2(r, r);
+    cpx ps = fast::fma2(fast::c_make(-1.95152959e-4f, -1.95152959e-4f), s2, fast::c_make(8.33216087e-3f, 8.33216087e-3f));
+    ps = fast::fma2(ps, s2, fast::c_make(-1.66666546e-1f, -1.66666546e-1f));
+    ps = fast::mul2(ps, s2);
+    const cpx sn = fast::fma2(ps, r, r);
+    cpx pc = fast::fma2(fast::c_make(2.44331571e-5f, 2.44331571e-5f), s2, fast::c_make(-1.38873163e-3f, -1.38873163e-3f));
+    pc = fast::fma2(pc, s2, fast::c_make(4.16666457e-2f, 4.16666457e-2f));
+    pc = fast::fma2(pc, s2, fast::c_make(-0.5f, -0.5f));
+    const cpx cs = fast::fma2(pc, s2, fast::c_make(1.f, 1.f));
+    auto quadrant = [](float sn_, float cs_, float kf, cpx& out) {
+        const int q = __float2int_rn(kf);
+        float so = (q & 1) ? cs_ : sn_;
+        float co = (q & 1) ? sn_ : cs_;
+        if (q & 2) so = -so;
+        if ((q + 1) & 2) co = -co;
+        out = fast::c_make(co, so);
+    };
+    quadrant(fast::c_re(sn), fast::c_re(cs), ka, ea);
+    quadrant(fast::c_im(sn), fast::c_im(cs), kb, eb);
+}
+
 // ---- row pass ------------------------------------------------------------------------------------------
 struct RowPassParams {
     float2* psi;                 // (n_img, nx, N) contiguous, transformed in place
@@ -122,8 +163,6 @@ struct RowCfg {
     static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + (size_t)N * sizeof(float2) + kWarps * 2 * sizeof(uint64_t);
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
 };
-
-using fast::cpx;
 
 template <int N>
 struct RowXchg {
@@ -197,16 +236,19 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = land_psi[c * N + j + e * C::T];
         }
-        __syncwarp();
-        if (lane == 0 && next) issue(un, true, false);
-        fast::line_fft<N, +1>(v, tw, j, xc, 0);
+        // The landing buffers go back to the async proxy only from inside the transforms, after the first
+        // exchange: its stores depend on every value loaded above, so the loads have completed by then.
+        // (Issuing right after a __syncwarp let the next unit's TMA overwrite words whose LDS was still in flight.)
+        fast::line_fft<N, +1>(v, tw, j, xc, 0, [&]() {
+            if (lane == 0 && next) issue(un, true, false);
+        });
         if constexpr (MODE == R_STEP) {
             mbar_wait(mb_t, parity);
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], land_t[c * N + j + e * C::T]);
-            __syncwarp();
-            if (lane == 0 && next) issue(un, false, true);
-            fast::line_fft<N, -1>(v, tw, j, xc, 0);
+            fast::line_fft<N, -1>(v, tw, j, xc, 0, [&]() {
+                if (lane == 0 && next) issue(un, false, true);
+            });
             cpx* dst = reinterpret_cast<cpx*>(p.psi) + u * C::kLand + c * N + j;
 #pragma unroll
             for (int e = 0; e < 16; ++e) dst[e * C::T] = v[e];
@@ -219,17 +261,17 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
             const long long img_elems = (long long)p.nx * N;
             const long long o = (fr * p.pair_nz + 2 * m) * img_elems + row * N + j;
             const bool has_b = 2 * m + 1 < p.pair_nz;
+            const cpx scale2 = fast::c_make(p.scale, p.scale), sigma2 = fast::c_make(p.sigma, p.sigma);
 #pragma unroll
             for (int e = 0; e < 16; ++e) {
-                const float va = fast::c_re(v[e]) * p.scale, vb = fast::c_im(v[e]) * p.scale;
-                float sn, cs;
-                sincosf(p.sigma * va, &sn, &cs);
-                p.t_out[o + e * C::T] = make_float2(cs, sn);
-                if (p.v_out) p.v_out[o + e * C::T] = va;
+                const cpx V2 = fast::mul2(v[e], scale2);         // (V_2m, V_2m+1)
+                cpx ta, tb;
+                pair_cis(fast::mul2(V2, sigma2), ta, tb);
+                reinterpret_cast<cpx*>(p.t_out)[o + e * C::T] = ta;
+                if (p.v_out) p.v_out[o + e * C::T] = fast::c_re(V2);
                 if (has_b) {
-                    sincosf(p.sigma * vb, &sn, &cs);
-                    p.t_out[o + img_elems + e * C::T] = make_float2(cs, sn);
-                    if (p.v_out) p.v_out[o + img_elems + e * C::T] = vb;
+                    reinterpret_cast<cpx*>(p.t_out)[o + img_elems + e * C::T] = tb;
+                    if (p.v_out) p.v_out[o + img_elems + e * C::T] = fast::c_im(V2);
                 }
             }
         }

@@ -23,6 +23,8 @@ struct BinParams {
     double inv_dz;          // 1 / (zs[1]-zs[0])
     double inv_lx, inv_ly;  // 1 / (nx*dx), 1 / (ny*dy)
     int* seg_of;            // (F, A, 2) segment ids (slice*ntypes + type) or -1
+    int* cursor;            // (F, nseg) fill counters of BinScatter (zeroed by the host)
+    int* unsorted;          // (F, cap) atom indices grouped by segment, arrival order
     int* offsets;           // (F, nseg+1): counts at [seg+1] after BinAssign, exclusive offsets after BinScan
     int* atom_list;         // (F, cap) atom indices grouped by segment, ascending inside a segment
     unsigned int* ux;       // (F, cap) frac(x/L) * 2^32
@@ -88,44 +90,54 @@ struct BinScan {
     }
 };
 
-// One CTA per (segment, frame): stable compaction of the atoms that belong to the segment, so the
-// list order (ascending atom index) -- and with it every float32 sum downstream -- is deterministic.
-struct BinCompact {
-    static constexpr int kThreads = 128;
+// Compaction in two steps.  BinScatter drops every (atom, hit) into its segment in arrival order (atomic
+// cursor per segment); BinOrder, one warp per (segment, frame), ranks the handful of atoms of the segment by
+// atom index and writes them out sorted together with their fixed-point x/y fractions, so the list order
+// (ascending atom index) -- and with it every float32 sum downstream -- is deterministic.
+struct BinScatter {
+    static constexpr int kThreads = 256;
     static constexpr int kMinBlocks = 1;
     template <class Ctx>
     static PSB_D void run(const Ctx& cx, const BinParams& p) {
-        const int seg = cx.bx(), f = cx.by();
+        const int a = cx.bx() * kThreads + cx.tid();
+        const int f = cx.by();
+        if (a >= p.A) return;
         const int nseg = p.nz * p.ntypes;
         const int* off = p.offsets + (long long)f * (nseg + 1);
-        const int begin = off[seg], count = off[seg + 1] - off[seg];
-        if (count == 0) return;                       // block-uniform
-        int* sm = reinterpret_cast<int*>(cx.smem());
-        const int t = cx.tid();
-        const int chunk = (p.A + kThreads - 1) / kThreads;
-        const int a0 = t * chunk;
-        const int a1 = a0 + chunk < p.A ? a0 + chunk : p.A;
-        const int* so = p.seg_of + (long long)f * p.A * 2;
-        int mine = 0;
-        for (int a = a0; a < a1; ++a) mine += (so[2 * a] == seg) + (so[2 * a + 1] == seg);
-        sm[t] = mine;
-        cx.sync();
-        int w = begin;
-        for (int k = 0; k < t; ++k) w += sm[k];
+        int* cur = p.cursor + (long long)f * nseg;
+        int* tmp = p.unsorted + (long long)f * p.cap;
+        for (int i = 0; i < 2; ++i) {
+            const int seg = p.seg_of[((long long)f * p.A + a) * 2 + i];
+            if (seg >= 0) tmp[off[seg] + cx.atomic_add(&cur[seg], 1)] = a;
+        }
+    }
+};
+
+struct BinOrder {
+    static constexpr int kThreads = 256;
+    static constexpr int kMinBlocks = 1;
+    template <class Ctx>
+    static PSB_D void run(const Ctx& cx, const BinParams& p) {
+        const int nseg = p.nz * p.ntypes;
+        const int seg = cx.bx() * (kThreads / 32) + cx.tid() / 32, f = cx.by();
+        if (seg >= nseg) return;
+        const int lane = cx.tid() % 32;
+        const int* off = p.offsets + (long long)f * (nseg + 1);
+        const int begin = off[seg], n = off[seg + 1] - off[seg];
+        const int* tmp = p.unsorted + (long long)f * p.cap + begin;
         const double* pos = p.pos + (long long)f * p.A * 3;
-        for (int a = a0; a < a1; ++a) {
-            const int hits = (so[2 * a] == seg) + (so[2 * a + 1] == seg);
-            for (int h = 0; h < hits; ++h) {
-                const long long o = (long long)f * p.cap + w;
-                p.atom_list[o] = a;
-                double u = pos[3 * a] * p.inv_lx;
-                double v = pos[3 * a + 1] * p.inv_ly;
-                u -= floor(u);
-                v -= floor(v);
-                p.ux[o] = (unsigned int)((unsigned long long)(u * 4294967296.0 + 0.5) & 0xffffffffull);
-                p.uy[o] = (unsigned int)((unsigned long long)(v * 4294967296.0 + 0.5) & 0xffffffffull);
-                ++w;
-            }
+        for (int i = lane; i < n; i += 32) {
+            const int a = tmp[i];
+            int rank = 0;
+            for (int k = 0; k < n; ++k) rank += tmp[k] < a;       // an atom occurs at most once per segment
+            const long long o = (long long)f * p.cap + begin + rank;
+            p.atom_list[o] = a;
+            double u = pos[3 * a] * p.inv_lx;
+            double v = pos[3 * a + 1] * p.inv_ly;
+            u -= floor(u);
+            v -= floor(v);
+            p.ux[o] = (unsigned int)((unsigned long long)(u * 4294967296.0 + 0.5) & 0xffffffffull);
+            p.uy[o] = (unsigned int)((unsigned long long)(v * 4294967296.0 + 0.5) & 0xffffffffull);
         }
     }
 };

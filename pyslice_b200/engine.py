@@ -23,7 +23,7 @@ PSI_BATCH_BYTES = 80 << 20
 T_BATCH_BYTES = 48 << 30
 # Workspace of the potential build (slice-paired spectra): chunks of this size flow through the three
 # potential kernels while staying L2-resident.
-SCRATCH_BYTES = 32 << 20
+SCRATCH_BYTES = 64 << 20
 
 
 class PhaseTimer:
@@ -184,7 +184,7 @@ def bin_atoms(plan: SlicePlan, positions: torch.Tensor):
     F, A, _ = positions.shape
     dev = plan.device
     nseg = plan.nz * plan.ntypes
-    seg = torch.empty((F, A, 2), dtype=torch.int32, device=dev)
+    seg = torch.empty((F * (4 * A + nseg),), dtype=torch.int32, device=dev)     # seg ids + unsorted lists + cursors
     offsets = torch.empty((F, nseg + 1), dtype=torch.int32, device=dev)
     atom_list = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
     ux = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)

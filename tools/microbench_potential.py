@@ -1,0 +1,39 @@
+"""Time psb_bin_atoms + psb_build_transmission on the C2 geometry for several scratch (chunk) sizes.
+usage: python tools/microbench_potential.py [frames] [scratch_MB ...]"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pyslice_b200 import engine, hostmath, synthetic
+
+F = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+sizes = [int(x) for x in sys.argv[2:]] or [32, 64, 96]
+traj = synthetic.silicon_trajectory(cells=(5, 5, 50), a=5.11, n_frames=F, seed=1, displacement="phonon")
+xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+pos = torch.from_numpy(traj.positions).cuda()
+tbuf = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device="cuda")
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+for fast in (True, False):
+    engine.set_fast_path(fast)
+    for mb in sizes:
+        engine.SCRATCH_BYTES = mb << 20
+        for _ in range(2):
+            engine.build_transmission(plan, pos, out=tbuf)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(3):
+            engine.build_transmission(plan, pos, out=tbuf)
+        b.record(); torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / 3
+        print(f"{'fused  ' if fast else 'generic'} scratch {mb:4d} MB  F={F}: {ms:8.3f} ms  {1e3*ms/(F*plan.nz):6.3f} us per slice  "
+              f"({F*plan.nz/ms/1e3:6.3f} M slices/s)", flush=True)
+    # binning alone
+    for _ in range(2):
+        engine.bin_atoms(plan, pos)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(5):
+        engine.bin_atoms(plan, pos)
+    b.record(); torch.cuda.synchronize()
+    print(f"   bin_atoms alone: {a.elapsed_time(b)/5:7.3f} ms", flush=True)
+engine.set_fast_path(True)
