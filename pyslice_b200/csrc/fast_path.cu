@@ -23,6 +23,7 @@
 // batch sizes engine.py picks), t is read once from HBM by the row pass.
 #include "fast_fft.cuh"
 #include "fast_path.h"
+#include "pdl.cuh"
 #include "psb_rt.h"
 #include "tables.h"
 
@@ -194,14 +195,16 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
         mbar_init(mb_t, 1);
         mbar_init_fence();
     }
+    pdl_trigger();
     if constexpr (MODE == R_STEP)
         for (int i = threadIdx.x; i < N; i += blockDim.x) spy[i] = reinterpret_cast<const cpx*>(p.py)[i];
-    __syncthreads();
 
     const int c = lane / C::T, j = lane % C::T;
     fast::Twiddles<N> tw;
     tw.load(p.tw, j);
     const RowXchg<N> xc{xb, c};
+    __syncthreads();
+    pdl_wait();          // everything above reads constant tables only; the images come from the previous kernel
 
     const uint64_t stream_once = l2_policy_evict_first();
     const long long GW = (long long)gridDim.x * C::kWarps;
@@ -343,13 +346,15 @@ __global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant
         mbar_init(mb, 1);
         mbar_init_fence();
     }
+    pdl_trigger();
     if constexpr (MODE == C_PROPAGATE)
         for (int i = tid; i < N; i += 256) spx[i] = reinterpret_cast<const cpx*>(p.px)[i];
-    __syncthreads();
 
     const int c = tid % C::W, j = tid / C::W;
     fast::Twiddles<N> tw;
     tw.load(p.tw, j);
+    __syncthreads();
+    pdl_wait();          // constant tables above, images below
     constexpr int kTilesPerImg = NY / C::W;
 
     long long tile = blockIdx.x;
@@ -449,9 +454,8 @@ int rows_go(const RowPassParams& p, cudaStream_t s) {
     long long want = (p.n_units + C::kWarps - 1) / C::kWarps;
     const int sms = rt::sm_count();
     const int grid = (int)(want < sms ? want : sms);
-    fast_rows_kernel<N, MODE><<<grid, 512, C::kSmem, s>>>(p);
+    cudaError_t e = pdl_launch(fast_rows_kernel<N, MODE>, dim3(grid), dim3(512), C::kSmem, s, p);
     ++launch_counter();
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast row pass launch: ") + cudaGetErrorString(e));
     return PSB_OK;
 }
@@ -480,9 +484,8 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* tw, cudaStre
     p.n_tiles = (long long)n_img * (NY / C::W);
     const long long slots = 2LL * rt::sm_count();
     const int grid = (int)(p.n_tiles < slots ? p.n_tiles : slots);
-    fast_cols_kernel<N, NY, MODE><<<grid, 256, C::kSmem, s>>>(map, p);
+    cudaError_t e = pdl_launch(fast_cols_kernel<N, NY, MODE>, dim3(grid), dim3(256), C::kSmem, s, map, p);
     ++launch_counter();
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast column pass launch: ") + cudaGetErrorString(e));
     return PSB_OK;
 }

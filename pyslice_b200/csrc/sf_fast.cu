@@ -17,6 +17,7 @@
 // The tables stay L2-resident between K1 and K2 (a few MB per chunk).
 #include "fast_fft.cuh"
 #include "fast_path.h"
+#include "pdl.cuh"
 #include "potential_kernels.cuh"
 #include "psb_rt.h"
 
@@ -87,6 +88,8 @@ __device__ __forceinline__ float2 slot_phase(int g, unsigned int u, int n, bool 
 
 // K1: one warp per atom entry of the chunk
 __global__ void __launch_bounds__(256) phase_tables_kernel(const SfFastParams p) {
+    pdl_trigger();
+    pdl_wait();          // the previous chunk's kernels may still be reading the tables
     const int fl = blockIdx.y;
     const int nseg = p.nz * p.ntypes;
     const int* off = p.offsets + (long long)fl * (nseg + 1);
@@ -171,12 +174,14 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
     const float* snx = p.snx + (long long)fl * p.cap;
     const float* sny = p.sny + (long long)fl * p.cap;
 
+    pdl_trigger();
     if (tid == 0) {
         mbar_init(&full[0], 1);
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();          // offsets / tables come from the previous kernels of the chain
 
     int gx[4], gy[2];
 #pragma unroll
@@ -379,12 +384,12 @@ int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned in
         ready = true;
     }
     if (cap > 0) {
-        phase_tables_kernel<<<dim3((cap + 7) / 8, nf), 256, 0, s>>>(p);
+        cudaError_t e1 = pdl_launch(phase_tables_kernel, dim3((cap + 7) / 8, nf), dim3(256), 0, s, p);
         ++launch_counter();
+        if (e1 != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("phase tables launch: ") + cudaGetErrorString(e1));
     }
-    sf_tiles_kernel<<<dim3(p.tiles_x * p.tiles_y, pair_count, nf), 256, kSfSmem, s>>>(p);
+    cudaError_t e = pdl_launch(sf_tiles_kernel, dim3(p.tiles_x * p.tiles_y, pair_count, nf), dim3(256), kSfSmem, s, p);
     ++launch_counter();
-    cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf fast launch: ") + cudaGetErrorString(e));
     return PSB_OK;
 }
