@@ -138,6 +138,12 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
     const int nseg = nz * ntypes;
     const int TXs = StructureFactorPaired::TX, TYs = StructureFactorPaired::TY;
     const int tiles = ((StructureFactorPaired::slots(nx) + TXs - 1) / TXs) * ((StructureFactorPaired::slots(ny) + TYs - 1) / TYs);
+#ifndef PSB_EMU
+    if (fast_path_enabled()) {
+        int rc0 = sf_fast_prepare(formfactors, ntypes, nx, ny, s);
+        if (rc0 != PSB_OK) return rc0;
+    }
+#endif
     for (int f0 = 0; f0 < n_frames; f0 += fc) {
         const int nf = n_frames - f0 < fc ? n_frames - f0 : fc;
         for (int mb = 0; mb < npairs; mb += mc) {
@@ -158,7 +164,7 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
             int rc;
 #ifndef PSB_EMU
             if (fast_path_enabled())
-                rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, formfactors, f2(scratch), s);
+                rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, f2(scratch), s);
             else
 #endif
             rc = go<StructureFactorPaired>(dim3(tiles, (unsigned)groups, nf), StructureFactorPaired::kSmem, s, sp, "structure_factor");
@@ -278,8 +284,7 @@ int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_p
     ex.out_elem_stride = ny; ex.out_line_stride = 1;
 
 #ifndef PSB_EMU
-    // fused persistent kernels for the steady state (fast_path.cu); the propagator is split Px -> column pass,
-    // Py -> next row pass, which is exact because no propagation follows the last slice
+    // fused persistent kernels for the steady state (fast_path.cu)
     const bool fast = fast_slice_supported(nx, ny);
 #else
     const bool fast = false;
@@ -290,8 +295,7 @@ int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_p
         int rc;
         if (z > 0 && fast) {
 #ifndef PSB_EMU
-            rc = launch_fast_rows(f2(psi_work), n_img, nx, ny, f2(t) + (long long)z * img, (long long)nz * img, n_probes,
-                                  f2(prop_y), s);
+            rc = launch_fast_rows(f2(psi_work), n_img, nx, ny, f2(t) + (long long)z * img, (long long)nz * img, n_probes, s);
 #endif
         } else if (z == 0) {
             row.src = f2(probes); row.src_img_stride = img; row.src_img_mod = n_probes;
@@ -311,7 +315,7 @@ int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_p
         }
         if (!last) {
 #ifndef PSB_EMU
-            if (fast) rc = launch_fast_cols(f2(psi_work), n_img, nx, ny, f2(prop_x), s);
+            if (fast) rc = launch_fast_cols(f2(psi_work), n_img, nx, ny, f2(prop_x), f2(prop_y), s);
             else
 #endif
             rc = launch_line_pass(PASS_C, col, n_img, s);

@@ -123,13 +123,17 @@ PSB_D void radix2(cpx& a0, cpx& a1) {
     a1 = d;
 }
 
-// 16-point DFT, natural order in and out (4 x 4 Cooley-Tukey: n = 4*n1 + n2, k = k1 + 4*k2)
-template <int DIR>
-PSB_D void radix16(cpx (&v)[16]) {
+// 16-point DFT (4 x 4 Cooley-Tukey: n = 4*n1 + n2, k = k1 + 4*k2) as a stream: `in(idx)` produces input idx when
+// the first butterfly layer needs it, `out(idx, value)` takes output idx as soon as the second layer has it.
+// Fusing the loads / pointwise multiplies / stores of a pass into these functors keeps only a few of the 16
+// values in flight around each memory operation; as separate 16-wide loops they made ptxas funnel every store
+// through one register pair (two MOVs per store and a serialised chain, ncu r1d/r1f).
+template <int DIR, class In, class Out>
+PSB_D void radix16_io(const In& in, const Out& out) {
     cpx a[4][4];   // a[n2][k1]
 #pragma unroll
     for (int n2 = 0; n2 < 4; ++n2) {
-        cpx t0 = v[n2], t1 = v[4 + n2], t2 = v[8 + n2], t3 = v[12 + n2];
+        cpx t0 = in(n2), t1 = in(4 + n2), t2 = in(8 + n2), t3 = in(12 + n2);
         radix4<DIR>(t0, t1, t2, t3);
         a[n2][0] = t0; a[n2][1] = t1; a[n2][2] = t2; a[n2][3] = t3;
     }
@@ -140,7 +144,7 @@ PSB_D void radix16(cpx (&v)[16]) {
     for (int k1 = 0; k1 < 4; ++k1) {
         cpx t0 = a[0][k1], t1 = a[1][k1], t2 = a[2][k1], t3 = a[3][k1];
         radix4<DIR>(t0, t1, t2, t3);
-        v[k1] = t0; v[k1 + 4] = t1; v[k1 + 8] = t2; v[k1 + 12] = t3;
+        out(k1, t0); out(k1 + 4, t1); out(k1 + 8, t2); out(k1 + 12, t3);
     }
 }
 
@@ -167,55 +171,68 @@ struct Twiddles {
     }
 };
 
+template <int N> constexpr int xi0_last() { return N == 512 ? 1 : 0; }
+
 // ---- the line transform -----------------------------------------------------------------------------
 // Xchg policy:  cpx* buf(int i)         exchange buffer of the i-th exchange of the current tile
 //               int at(int q)           element index of position q of this thread's line in that buffer
 //               void after_store(int i) all stores of exchange i visible to the line's threads
 //               void after_load(int i)  all loads of exchange i done (buffer reusable)
+// in(e)  -> the thread's input at position j + e*T (e = 0..15), called once per e while the first stage runs
+// out(e, value) <- the transform at position j + e*T, called once per e while the last stage runs
 // `hook()` runs right after the first exchange's stores are visible: by then every thread of the line's
-// sync scope has CONSUMED the values it held on entry (the stores depend on them), which is the earliest
-// point at which the buffer those values were loaded from may be handed back to the async proxy.
+// sync scope has CONSUMED what `in` gave it (the stores depend on it), which is the earliest point at which
+// the buffer `in` read from may be handed back to the async proxy.
+// `before_last()` runs before the last stage starts calling `out` (e.g. wait for the operand `out` multiplies by).
 struct NoHook {
     PSB_D void operator()() const {}
 };
 
-template <int N, int DIR, class Xchg, class Hook = NoHook>
-PSB_D void line_fft(cpx (&v)[16], const Twiddles<N>& tw, int j, const Xchg& x, int xi0, const Hook& hook = Hook()) {
+template <int N, int DIR, class In, class Out, class Xchg, class Hook = NoHook, class Hook2 = NoHook>
+PSB_D void line_fft(const In& in, const Out& out, const Twiddles<N>& tw, int j, const Xchg& x, int xi0,
+                    const Hook& hook = Hook(), const Hook2& before_last = Hook2()) {
     constexpr int T = N / 16;
     // stage 1: radix 16 over positions j + t*T, outputs to 16*j + u
-    radix16<DIR>(v);
     {
         cpx* sm = x.buf(xi0);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) sm[x.at(16 * j + u)] = v[u];
+        radix16_io<DIR>(in, [&](int u, cpx val) { sm[x.at(16 * j + u)] = val; });
         x.after_store(xi0);
         hook();
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = sm[x.at(j + e * T)];
-        x.after_load(xi0);
     }
     if constexpr (N == 512) {
-        // stage 2: radix 2, NS = 16: butterfly m pairs v[m], v[m + 8] (positions b, b + 256 with b = j + 32*m),
-        // twiddle exp(-+2*pi*i*(b & 15)/32) = w2, outputs to (b/16)*32 + (b & 15) + u*16
-        cpx* sm = x.buf(xi0 + 1);
+        // stage 2: radix 2, NS = 16: butterfly m pairs positions b, b + 256 (b = j + 32*m), twiddle
+        // exp(-+2*pi*i*(b & 15)/32) = w2, outputs to (b/16)*32 + (b & 15) + u*16
+        // (all 16 loads complete before the first store: the two exchanges may share one buffer)
+        const cpx* s1 = x.buf(xi0);
+        cpx* s2 = x.buf(xi0 + 1);
+        cpx v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = s1[x.at(j + e * T)];
+        x.after_load(xi0);
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
-            cpx a0 = v[m], a1 = DIR < 0 ? cmulp(v[m + 8], tw.w2) : cmulcp(v[m + 8], tw.w2);
+            cpx a0 = v[m];
+            cpx a1 = DIR < 0 ? cmulp(v[m + 8], tw.w2) : cmulcp(v[m + 8], tw.w2);
             radix2<DIR>(a0, a1);
             const int b = j + 32 * m;
             const int q0 = (b >> 4) * 32 + (b & 15);
-            sm[x.at(q0)] = a0;
-            sm[x.at(q0 + 16)] = a1;
+            s2[x.at(q0)] = a0;
+            s2[x.at(q0 + 16)] = a1;
         }
         x.after_store(xi0 + 1);
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = sm[x.at(j + e * T)];
-        x.after_load(xi0 + 1);
     }
-    // last stage: radix 16 with the thread's own twiddles; outputs land in natural strided order
-#pragma unroll
-    for (int t = 1; t < 16; ++t) v[t] = DIR < 0 ? cmulp(v[t], tw.w[t - 1]) : cmulcp(v[t], tw.w[t - 1]);
-    radix16<DIR>(v);
+    // last stage: radix 16 with the thread's own twiddles; outputs come out in natural strided order
+    constexpr int xl = xi0_last<N>();
+    const cpx* sl = x.buf(xi0 + xl);
+    before_last();
+    radix16_io<DIR>(
+        [&](int t) {
+            const cpx a = sl[x.at(j + t * T)];
+            if (t == 0) return a;
+            return DIR < 0 ? cmulp(a, tw.w[t > 0 ? t - 1 : 0]) : cmulcp(a, tw.w[t > 0 ? t - 1 : 0]);
+        },
+        out);
+    x.after_load(xi0 + xl);
 }
 
 // number of shared-memory exchanges of one line transform

@@ -1,11 +1,12 @@
 // Fused slice-step kernels for 256- and 512-point lines: the steady state of psb_propagate
 // (reference: src/multislice/multislice.py:281-294, one loop iteration = one row pass + one column pass).
 //
-//   row pass   psi[x, ky] -> FFT_y( t_s[x, y] * IFFT_y( Py[ky] * psi[x, ky] ) )        (in place)
-//   col pass   psi[x, ky] -> IFFT_x( Px[kx] * FFT_x( psi[x, ky] ) )                     (in place)
+//   row pass   psi[x, ky] -> FFT_y( t_s[x, y] * IFFT_y( psi[x, ky] ) )                  (in place)
+//   col pass   psi[x, ky] -> IFFT_x( Px[kx] * FFT_x( Py[ky] * psi[x, ky] ) )            (in place)
 //
-// with the Fresnel propagator split as P[kx, ky] = Px[kx] * Py[ky] (Py commutes with the x transforms, so
-// it is applied where ky runs along the line).  Both are persistent kernels sized to the SM count:
+// with the Fresnel propagator split as P[kx, ky] = Px[kx] * Py[ky]; Py commutes with the x transforms and ky is
+// the column a thread of the column pass owns, so it is one register per tile there (applied on load).
+// Both are persistent kernels sized to the SM count:
 //
 //   * inputs arrive through the async proxy: cp.async.bulk (TMA, 1-D) global -> shared, completion on an
 //     mbarrier; the copy for the NEXT tile is issued as soon as the current tile's landing buffer has been
@@ -97,14 +98,20 @@ __device__ __forceinline__ void tensor2d_g2s(void* dst, const CUtensorMap* map, 
 // the paired inverse transform).  Cody-Waite reduction by pi/2 in two steps and the degree-7 / degree-8 minimax
 // polynomials on [-pi/4, pi/4], evaluated with packed FMAs; measured max abs error 8.3e-8 for |x| <= 40 against
 // float64 (tools/diag notes in DESIGN.md).  |x| >= 256 takes libdevice's sincosf (never seen: x = sigma*V ~ a few rad).
+__device__ __noinline__ void pair_cis_slow(float xa, float xb, float* out4) {      // kept out of line: 32 inlined
+    float s, c;                                                                     // copies of libdevice's slow path
+    sincosf(xa, &s, &c);                                                            // would not fit the I-cache
+    out4[0] = c; out4[1] = s;
+    sincosf(xb, &s, &c);
+    out4[2] = c; out4[3] = s;
+}
 __device__ __forceinline__ void pair_cis(cpx x, cpx& ea, cpx& eb) {
     const float xa = fast::c_re(x), xb = fast::c_im(x);
     if (fabsf(xa) >= 256.f || fabsf(xb) >= 256.f) {
-        float s, c;
-        sincosf(xa, &s, &c);
-        ea = fast::c_make(c, s);
-        sincosf(xb, &s, &c);
-        eb = fast::c_make(c, s);
+        float o[4];
+        pair_cis_slow(xa, xb, o);
+        ea = fast::c_make(o[0], o[1]);
+        eb = fast::c_make(o[2], o[3]);
         return;
     }
     const float ka = rintf(xa * 0.63661977236758134f), kb = rintf(xb * 0.63661977236758134f);
@@ -139,7 +146,6 @@ struct RowPassParams {
     long long t_frame_stride;    // elements between consecutive frames of t
     int probes;                  // images per frame (image = frame*probes + probe)
     int nx;                      // lines per image
-    const float2* py;            // [N] propagator factor along the line
     const float2* tw;            // staged twiddle table of Plan<N, 16>
     long long n_units;           // n_img * nx / lines-per-warp
     // R_TRANSMIT: image = frame*pair_count + ml holds V_{2m} + i*V_{2m+1}, m = pair_begin + ml; the transmission
@@ -161,7 +167,7 @@ struct RowCfg {
     static constexpr int kLand = LPW * N;          // float2 per landing buffer (4 KB)
     static constexpr int kX = LPW * NP;
     static constexpr int kWarpElems = 2 * kLand + kX;
-    static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + (size_t)N * sizeof(float2) + kWarps * 2 * sizeof(uint64_t);
+    static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + kWarps * 2 * sizeof(uint64_t);
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
 };
 
@@ -185,8 +191,7 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
     cpx* land_psi = sm + (size_t)warp * C::kWarpElems;
     cpx* land_t = land_psi + C::kLand;
     cpx* xb = land_t + C::kLand;
-    cpx* spy = sm + (size_t)C::kWarps * C::kWarpElems;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(spy + N) + 2 * warp;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)C::kWarps * C::kWarpElems) + 2 * warp;
     uint64_t* mb_psi = bars;
     uint64_t* mb_t = bars + 1;
 
@@ -196,9 +201,6 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
         mbar_init_fence();
     }
     pdl_trigger();
-    if constexpr (MODE == R_STEP)
-        for (int i = threadIdx.x; i < N; i += blockDim.x) spy[i] = reinterpret_cast<const cpx*>(p.py)[i];
-
     const int c = lane / C::T, j = lane % C::T;
     fast::Twiddles<N> tw;
     tw.load(p.tw, j);
@@ -207,76 +209,82 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
     pdl_wait();          // everything above reads constant tables only; the images come from the previous kernel
 
     const uint64_t stream_once = l2_policy_evict_first();
-    const long long GW = (long long)gridDim.x * C::kWarps;
-    long long u = (long long)blockIdx.x * C::kWarps + warp;
-    const int units_per_img = p.nx / C::LPW;
+    // unit / image arithmetic in 32 bits with shifts: nx is 256 or 512 here, n_units < 2^31 (64-bit division is
+    // a ~100-instruction subroutine, and it sat in every prefetch)
+    const int GW = (int)gridDim.x * C::kWarps;
+    int u = (int)blockIdx.x * C::kWarps + warp;
+    const int n_units = (int)p.n_units;
+    const int upi_shift = 31 - __clz(p.nx / C::LPW);          // log2(units per image)
+    const int upi_mask = (1 << upi_shift) - 1;
 
-    auto issue = [&](long long unit, bool want_psi, bool want_t) {
+    auto issue = [&](int unit, bool want_psi, bool want_t) {
         if (want_psi) {
             mbar_expect_tx(mb_psi, C::kBytes);
-            bulk_g2s(land_psi, p.psi + unit * C::kLand, C::kBytes, mb_psi);
+            bulk_g2s(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi);
         }
         if (MODE == R_STEP && want_t) {
-            const long long img = unit / units_per_img;
-            const long long row0 = (unit % units_per_img) * C::LPW;
-            const float2* src = p.t + (img / p.probes) * p.t_frame_stride + row0 * N;
+            const unsigned img = (unsigned)unit >> upi_shift;
+            const int row0 = (unit & upi_mask) * C::LPW;
+            const float2* src = p.t + (long long)(img / (unsigned)p.probes) * p.t_frame_stride + row0 * N;
             mbar_expect_tx(mb_t, C::kBytes);
             bulk_g2s_hint(land_t, src, C::kBytes, mb_t, stream_once);
         }
     };
-    if (u < p.n_units && lane == 0) issue(u, true, true);
+    if (u < n_units && lane == 0) issue(u, true, true);
 
-    for (uint32_t it = 0; u < p.n_units; u += GW, ++it) {
+    for (uint32_t it = 0; u < n_units; u += GW, ++it) {
         const uint32_t parity = it & 1u;
-        const long long un = u + GW;
-        const bool next = un < p.n_units;
-        cpx v[16];
+        const int un = u + GW;
+        const bool next = un < n_units;
         mbar_wait(mb_psi, parity);
-        if constexpr (MODE == R_STEP) {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(land_psi[c * N + j + e * C::T], spy[j + e * C::T]);
-        } else {
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = land_psi[c * N + j + e * C::T];
-        }
         // The landing buffers go back to the async proxy only from inside the transforms, after the first
-        // exchange: its stores depend on every value loaded above, so the loads have completed by then.
+        // exchange: its stores depend on every value loaded from them, so those loads have completed by then.
         // (Issuing right after a __syncwarp let the next unit's TMA overwrite words whose LDS was still in flight.)
-        fast::line_fft<N, +1>(v, tw, j, xc, 0, [&]() {
-            if (lane == 0 && next) issue(un, true, false);
-        });
+        const cpx* lp = land_psi + c * N + j;
+        const cpx* lt = land_t + c * N + j;
         if constexpr (MODE == R_STEP) {
-            mbar_wait(mb_t, parity);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], land_t[c * N + j + e * C::T]);
-            fast::line_fft<N, -1>(v, tw, j, xc, 0, [&]() {
+            cpx v[16];
+            // psi[x, ky] -> IFFT_y -> * t[x, y]
+            fast::line_fft<N, +1>(
+                [&](int e) { return lp[e * C::T]; },
+                [&](int e, cpx a) { v[e] = fast::cmulp(a, lt[e * C::T]); }, tw, j, xc, 0,
+                [&]() {
+                    if (lane == 0 && next) issue(un, true, false);
+                },
+                [&]() { mbar_wait(mb_t, parity); });
+            // -> FFT_y -> global
+            cpx* dst = reinterpret_cast<cpx*>(p.psi) + (long long)u * C::kLand + c * N + j;
+            fast::line_fft<N, -1>([&](int e) { return v[e]; }, [&](int e, cpx a) { dst[e * C::T] = a; }, tw, j, xc, 0, [&]() {
                 if (lane == 0 && next) issue(un, false, true);
             });
-            cpx* dst = reinterpret_cast<cpx*>(p.psi) + u * C::kLand + c * N + j;
-#pragma unroll
-            for (int e = 0; e < 16; ++e) dst[e * C::T] = v[e];
         } else {
             // potentials.py:336-342 + multislice.py:281-282: V = Re/Im(IFFT2) * scale, t = exp(i*sigma*V), two slices per image
-            const long long img = u / units_per_img;
-            const long long row = (u % units_per_img) * C::LPW + c;
-            const long long fr = img / p.pair_count;
-            const int m = p.pair_begin + (int)(img % p.pair_count);
+            const unsigned img = (unsigned)u >> upi_shift;
+            const int row = (u & upi_mask) * C::LPW + c;
+            const unsigned fr = img / (unsigned)p.pair_count;
+            const int m = p.pair_begin + (int)(img - fr * (unsigned)p.pair_count);
             const long long img_elems = (long long)p.nx * N;
-            const long long o = (fr * p.pair_nz + 2 * m) * img_elems + row * N + j;
+            const long long o = ((long long)fr * p.pair_nz + 2 * m) * img_elems + row * N + j;
             const bool has_b = 2 * m + 1 < p.pair_nz;
             const cpx scale2 = fast::c_make(p.scale, p.scale), sigma2 = fast::c_make(p.sigma, p.sigma);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) {
-                const cpx V2 = fast::mul2(v[e], scale2);         // (V_2m, V_2m+1)
-                cpx ta, tb;
-                pair_cis(fast::mul2(V2, sigma2), ta, tb);
-                reinterpret_cast<cpx*>(p.t_out)[o + e * C::T] = ta;
-                if (p.v_out) p.v_out[o + e * C::T] = fast::c_re(V2);
-                if (has_b) {
-                    reinterpret_cast<cpx*>(p.t_out)[o + img_elems + e * C::T] = tb;
-                    if (p.v_out) p.v_out[o + img_elems + e * C::T] = fast::c_im(V2);
-                }
-            }
+            cpx* ta_out = reinterpret_cast<cpx*>(p.t_out) + o;
+            fast::line_fft<N, +1>(
+                [&](int e) { return lp[e * C::T]; },
+                [&](int e, cpx a) {
+                    const cpx V2 = fast::mul2(a, scale2);         // (V_2m, V_2m+1)
+                    cpx ta, tb;
+                    pair_cis(fast::mul2(V2, sigma2), ta, tb);
+                    ta_out[e * C::T] = ta;
+                    if (p.v_out) p.v_out[o + e * C::T] = fast::c_re(V2);
+                    if (has_b) {
+                        ta_out[img_elems + e * C::T] = tb;
+                        if (p.v_out) p.v_out[o + img_elems + e * C::T] = fast::c_im(V2);
+                    }
+                },
+                tw, j, xc, 0,
+                [&]() {
+                    if (lane == 0 && next) issue(un, true, false);
+                });
         }
     }
 }
@@ -285,6 +293,7 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
 struct ColPassParams {
     float2* psi;                 // (n_img, N, NY) contiguous, transformed in place along the first image axis
     const float2* px;            // [N] propagator factor along the line (includes 1/(nx*ny))
+    const float2* py;            // [NY] propagator factor of the column (C_PROPAGATE)
     const float2* tw;
     long long n_tiles;           // n_img * NY / W
 };
@@ -296,7 +305,7 @@ struct ColCfg {
     static constexpr int kPadRows = (W == 8) ? N / 16 : 0;            // keeps 8-column rows conflict-free
     static constexpr int kLand = N * W;                               // float2 (32 KB)
     static constexpr int kX = (N + kPadRows) * W;
-    static constexpr size_t kSmem = (size_t)(kLand + 2 * kX + N) * sizeof(float2) + 2 * sizeof(uint64_t);
+    static constexpr size_t kSmem = (size_t)(kLand + 2 * kX + N) * sizeof(float2) + 2 * sizeof(uint64_t);      // + NY*8 for Py, added at launch
     static constexpr int kBoxRows = 256;                              // TMA box limit per dimension
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
 };
@@ -339,7 +348,8 @@ __global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant
     cpx* xb0 = land + C::kLand;
     cpx* xb1 = xb0 + C::kX;
     cpx* spx = xb1 + C::kX;
-    uint64_t* mb = reinterpret_cast<uint64_t*>(spx + N);
+    cpx* spy = spx + N;
+    uint64_t* mb = reinterpret_cast<uint64_t*>(spy + NY);
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -347,8 +357,10 @@ __global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant
         mbar_init_fence();
     }
     pdl_trigger();
-    if constexpr (MODE == C_PROPAGATE)
+    if constexpr (MODE == C_PROPAGATE) {
         for (int i = tid; i < N; i += 256) spx[i] = reinterpret_cast<const cpx*>(p.px)[i];
+        for (int i = tid; i < NY; i += 256) spy[i] = reinterpret_cast<const cpx*>(p.py)[i];
+    }
 
     const int c = tid % C::W, j = tid / C::W;
     fast::Twiddles<N> tw;
@@ -376,24 +388,25 @@ __global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant
             xc.next_c0 = -1;
         }
         mbar_wait(mb, it & 1u);
-        cpx v[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = land[(j + e * C::T) * C::W + c];
+        const cpx* lp = land + j * C::W + c;
+        cpx* dst = reinterpret_cast<cpx*>(p.psi) + (tile / kTilesPerImg) * ((long long)N * NY) + (tile % kTilesPerImg) * C::W + j * NY + c;
         if constexpr (MODE == C_PROPAGATE) {
-            fast::line_fft<N, -1>(v, tw, j, xc, 0);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = fast::cmulp(v[e], spx[j + e * C::T]);
+            cpx v[16];
+            // * Py[ky] -> FFT_x -> * Px[kx] -> IFFT_x
+            xc.hook_i = 0;
+            const cpx pyc = spy[(int)(tile % kTilesPerImg) * C::W + c];
+            fast::line_fft<N, -1>([&](int e) { return fast::cmulp(lp[e * C::T * C::W], pyc); },
+                                  [&](int e, cpx a) { v[e] = fast::cmulp(a, spx[j + e * C::T]); }, tw, j, xc, 0);
             xc.next_c0 = -1;
-            fast::line_fft<N, +1>(v, tw, j, xc, fast::exchanges<N>());
+            fast::line_fft<N, +1>([&](int e) { return v[e]; }, [&](int e, cpx a) { dst[e * C::T * NY] = a; }, tw, j, xc,
+                                  fast::exchanges<N>());
         } else {
             // one transform per tile: alternate the exchange buffer between tiles so a single barrier per
             // exchange still orders the reuse (N = 512 already alternates inside the transform)
             xc.hook_i = fast::exchanges<N>() == 1 ? (int)(it & 1u) : 0;
-            fast::line_fft<N, +1>(v, tw, j, xc, xc.hook_i);
+            fast::line_fft<N, +1>([&](int e) { return lp[e * C::T * C::W]; }, [&](int e, cpx a) { dst[e * C::T * NY] = a; }, tw, j,
+                                  xc, xc.hook_i);
         }
-        cpx* dst = reinterpret_cast<cpx*>(p.psi) + (tile / kTilesPerImg) * ((long long)N * NY) + (tile % kTilesPerImg) * C::W + j * NY + c;
-#pragma unroll
-        for (int e = 0; e < 16; ++e) dst[e * C::T * NY] = v[e];
     }
 }
 
@@ -461,11 +474,11 @@ int rows_go(const RowPassParams& p, cudaStream_t s) {
 }
 
 template <int N, int NY, int MODE>
-int cols_go(float2* psi, int n_img, const float2* px, const float2* tw, cudaStream_t s) {
+int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const float2* tw, cudaStream_t s) {
     using C = ColCfg<N>;
     static bool ready = false;
     if (!ready) {
-        int rc = ensure_smem(fast_cols_kernel<N, NY, MODE>, C::kSmem, "fast column pass");
+        int rc = ensure_smem(fast_cols_kernel<N, NY, MODE>, C::kSmem + NY * sizeof(float2), "fast column pass");
         if (rc != PSB_OK) return rc;
         ready = true;
     }
@@ -480,11 +493,11 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* tw, cudaStre
         map_img = n_img;
     }
     ColPassParams p;
-    p.psi = psi; p.px = px; p.tw = tw;
+    p.psi = psi; p.px = px; p.py = py; p.tw = tw;
     p.n_tiles = (long long)n_img * (NY / C::W);
     const long long slots = 2LL * rt::sm_count();
     const int grid = (int)(p.n_tiles < slots ? p.n_tiles : slots);
-    cudaError_t e = pdl_launch(fast_cols_kernel<N, NY, MODE>, dim3(grid), dim3(256), C::kSmem, s, map, p);
+    cudaError_t e = pdl_launch(fast_cols_kernel<N, NY, MODE>, dim3(grid), dim3(256), C::kSmem + NY * sizeof(float2), s, map, p);
     ++launch_counter();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast column pass launch: ") + cudaGetErrorString(e));
     return PSB_OK;
@@ -501,10 +514,10 @@ bool fast_slice_supported(int nx, int ny) {
 }
 
 int launch_fast_rows(float2* psi, int n_img, int nx, int ny, const float2* t_slice, long long t_frame_stride,
-                     int probes, const float2* py, cudaStream_t s) {
+                     int probes, cudaStream_t s) {
     RowPassParams p;
     std::memset(&p, 0, sizeof(p));
-    p.psi = psi; p.t = t_slice; p.t_frame_stride = t_frame_stride; p.probes = probes; p.nx = nx; p.py = py;
+    p.psi = psi; p.t = t_slice; p.t_frame_stride = t_frame_stride; p.probes = probes; p.nx = nx;
     int rc = twiddles_for(ny, &p.tw, s);
     if (rc != PSB_OK) return rc;
     if (ny == 256) {
@@ -533,23 +546,23 @@ int launch_fast_rows_transmit(float2* pairs, int n_img, int nx, int ny, float sc
 }
 
 template <int MODE>
-static int cols_dispatch(float2* psi, int n_img, int nx, int ny, const float2* px, cudaStream_t s) {
+static int cols_dispatch(float2* psi, int n_img, int nx, int ny, const float2* px, const float2* py, cudaStream_t s) {
     const float2* tw = nullptr;
     int rc = twiddles_for(nx, &tw, s);
     if (rc != PSB_OK) return rc;
-    if (nx == 256 && ny == 256) return cols_go<256, 256, MODE>(psi, n_img, px, tw, s);
-    if (nx == 256 && ny == 512) return cols_go<256, 512, MODE>(psi, n_img, px, tw, s);
-    if (nx == 512 && ny == 256) return cols_go<512, 256, MODE>(psi, n_img, px, tw, s);
-    if (nx == 512 && ny == 512) return cols_go<512, 512, MODE>(psi, n_img, px, tw, s);
+    if (nx == 256 && ny == 256) return cols_go<256, 256, MODE>(psi, n_img, px, py, tw, s);
+    if (nx == 256 && ny == 512) return cols_go<256, 512, MODE>(psi, n_img, px, py, tw, s);
+    if (nx == 512 && ny == 256) return cols_go<512, 256, MODE>(psi, n_img, px, py, tw, s);
+    if (nx == 512 && ny == 512) return cols_go<512, 512, MODE>(psi, n_img, px, py, tw, s);
     return fail(PSB_ERR_UNSUPPORTED, "fast column pass: unsupported grid");
 }
 
-int launch_fast_cols(float2* psi, int n_img, int nx, int ny, const float2* px, cudaStream_t s) {
-    return cols_dispatch<C_PROPAGATE>(psi, n_img, nx, ny, px, s);
+int launch_fast_cols(float2* psi, int n_img, int nx, int ny, const float2* px, const float2* py, cudaStream_t s) {
+    return cols_dispatch<C_PROPAGATE>(psi, n_img, nx, ny, px, py, s);
 }
 
 int launch_fast_cols_inverse(float2* imgs, int n_img, int nx, int ny, cudaStream_t s) {
-    return cols_dispatch<C_INVERSE>(imgs, n_img, nx, ny, nullptr, s);
+    return cols_dispatch<C_INVERSE>(imgs, n_img, nx, ny, nullptr, nullptr, s);
 }
 
 }  // namespace psb

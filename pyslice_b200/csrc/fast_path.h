@@ -9,12 +9,12 @@ bool fast_slice_supported(int nx, int ny);
 void fast_path_enable(int on);
 bool fast_path_enabled();
 
-// psi[x, ky] -> FFT_y( t[x, y] * IFFT_y( py[ky] * psi[x, ky] ) ) in place over n_img contiguous (nx, ny) images;
+// psi[x, ky] -> FFT_y( t[x, y] * IFFT_y( psi[x, ky] ) ) in place over n_img contiguous (nx, ny) images;
 // image i uses the transmission slice t_slice + (i / probes) * t_frame_stride.
 int launch_fast_rows(float2* psi, int n_img, int nx, int ny, const float2* t_slice, long long t_frame_stride,
-                     int probes, const float2* py, cudaStream_t s);
-// psi[x, ky] -> IFFT_x( px[kx] * FFT_x( psi[x, ky] ) ) in place (unnormalised; px carries the 1/(nx*ny)).
-int launch_fast_cols(float2* psi, int n_img, int nx, int ny, const float2* px, cudaStream_t s);
+                     int probes, cudaStream_t s);
+// psi[x, ky] -> IFFT_x( px[kx] * py[ky] * FFT_x( psi[x, ky] ) ) in place (unnormalised; px carries the 1/(nx*ny)).
+int launch_fast_cols(float2* psi, int n_img, int nx, int ny, const float2* px, const float2* py, cudaStream_t s);
 
 // potential build (potentials.py:336-342): in-place inverse column transform of n_img slice-pair spectra, then
 // inverse row transform with the transmission epilogue t = exp(i*sigma*scale*Re/Im(.)) for the two slices of a pair
@@ -24,8 +24,10 @@ int launch_fast_rows_transmit(float2* pairs, int n_img, int nx, int ny, float sc
 
 // structure-factor sum of slice pairs [pair_begin, pair_begin + pair_count) of nf frames into out (nf, pair_count, nx, ny)
 // (sf_fast.cu: precomputed phase tables + TMA-fed packed-FMA tiles); any grid size
+// sf_fast_prepare gathers the form-factor table once per psb_build_transmission call; launch_sf_fast runs per chunk
+int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s);
 int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
-                   int ny, int pair_begin, int pair_count, int nf, const float* ff, float2* out, cudaStream_t s);
+                   int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s);
 void sf_fast_release();
 
 }  // namespace psb

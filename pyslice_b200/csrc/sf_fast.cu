@@ -70,7 +70,7 @@ struct SfFastParams {
     float2* taby;               // [nf][tiles_y][cap][TY]
     float* snx;                 // [nf][cap]  Nyquist sine (corner term), even axes only
     float* sny;
-    const float* ff;            // (ntypes, nx, ny)
+    const float4* ff4;          // (ntypes, nsx, nsy): form factor at the four table positions a slot's sums need
     float2* out;                // (nf, pair_count, nx, ny)
 };
 
@@ -84,6 +84,21 @@ __device__ __forceinline__ float2 slot_phase(int g, unsigned int u, int n, bool 
         *sn_out = q.y;
     }
     return z;
+}
+
+// K0 (once per psb_build_transmission call): gather the form factor for the four real sums of every slot
+//   .x -> cc at (kx, ky)   .y -> ss at (kx', ky')   .z -> cs at (kx, ky')   .w -> sc at (kx', ky)
+// where kx' = kx except for slot 0 of an even axis, whose sine component carries the Nyquist line (kx' = n/2)
+__global__ void __launch_bounds__(256) ff4_kernel(const float* ff, float4* ff4, int ntypes, int nx, int ny) {
+    const int nsx = StructureFactorPaired::slots(nx), nsy = StructureFactorPaired::slots(ny);
+    const long long n = (long long)ntypes * nsx * nsy;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int gy = (int)(i % nsy), gx = (int)((i / nsy) % nsx), t = (int)(i / ((long long)nsx * nsy));
+        const int fx1 = (gx == 0 && nx % 2 == 0) ? nx / 2 : gx, fy1 = (gy == 0 && ny % 2 == 0) ? ny / 2 : gy;
+        const float* f = ff + (long long)t * nx * ny;
+        ff4[i] = make_float4(f[(long long)gx * ny + gy], f[(long long)fx1 * ny + fy1], f[(long long)gx * ny + fy1],
+                             f[(long long)fx1 * ny + gy]);
+    }
 }
 
 // K1: one warp per atom entry of the chunk
@@ -151,14 +166,13 @@ __device__ __forceinline__ void iter_next(BlockIter& it, const int* off, int m, 
 }
 
 constexpr int kStageElems = CH * (TX + TY);
-constexpr size_t kSfSmem = 2 * (size_t)kStageElems * sizeof(float2) + 32 * 256 * sizeof(float) + 2 * sizeof(uint64_t);
+constexpr size_t kSfSmem = 2 * (size_t)kStageElems * sizeof(float2) + 2 * sizeof(uint64_t);
 
 // K2
 __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* stage = reinterpret_cast<cpx*>(smem_raw);                         // [2][CH*TX + CH*TY]
-    float* stash = reinterpret_cast<float*>(stage + 2 * kStageElems);      // [32][256]
-    uint64_t* full = reinterpret_cast<uint64_t*>(stash + 32 * 256);        // [2]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + 2 * kStageElems); // [2]
 
     const int nsx = StructureFactorPaired::slots(p.nx), nsy = StructureFactorPaired::slots(p.ny);
     const int tile_x = blockIdx.x / p.tiles_y, tile_y = blockIdx.x % p.tiles_y;
@@ -211,6 +225,7 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
 
     int used = 0;
     float tot[4][2][4];     // [i][k][cc, ss, cs, sc], multiplied by the form factor
+    float first[4][2][4];   // the pair's first slice while the second one accumulates
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -261,22 +276,21 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
                     ++used;
                     issue();                     // refill it with the block after the one already in flight
                 }
-                const float* ff = p.ff + (long long)t * p.nx * p.ny;
+                const float4* ff4 = p.ff4 + (long long)t * nsx * nsy;
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int k = 0; k < 2; ++k) {
                         if (gx[i] < nsx && gy[k] < nsy) {
-                            const int fx0 = gx[i], fx1 = (gx[i] == 0 && nq_x) ? p.nx / 2 : gx[i];
-                            const int fy0 = gy[k], fy1 = (gy[k] == 0 && nq_y) ? p.ny / 2 : gy[k];
+                            const float4 f = __ldg(&ff4[gx[i] * nsy + gy[k]]);
                             const float cc = fast::c_re(P[i][k]), cs = fast::c_im(P[i][k]);
                             const float sc = fast::c_re(Q[i][k]);
                             float ss = fast::c_im(Q[i][k]);
                             if (corner_tile && gx[i] == 0 && gy[k] == 0) ss -= corr;
-                            tot[i][k][0] += cc * __ldg(&ff[(long long)fx0 * p.ny + fy0]);
-                            tot[i][k][1] += ss * __ldg(&ff[(long long)fx1 * p.ny + fy1]);
-                            tot[i][k][2] += cs * __ldg(&ff[(long long)fx0 * p.ny + fy1]);
-                            tot[i][k][3] += sc * __ldg(&ff[(long long)fx1 * p.ny + fy0]);
+                            tot[i][k][0] += cc * f.x;
+                            tot[i][k][1] += ss * f.y;
+                            tot[i][k][2] += cs * f.z;
+                            tot[i][k][3] += sc * f.w;
                         }
                     }
             }
@@ -287,13 +301,13 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) stash[((i * 2 + k) * 4 + q) * 256 + tid] = tot[i][k][q];
+                    for (int q = 0; q < 4; ++q) first[i][k][q] = tot[i][k][q];
         }
     }
-    // tot = second slice (B), stash = first slice (A):  Z = S'_A + i*S'_B at up to four mirror positions
+    // tot = second slice (B), first = first slice (A):  Z = S'_A + i*S'_B at up to four mirror positions
     float2* out = p.out + ((long long)fl * p.pair_count + ml) * p.nx * p.ny;
     auto emit = [&](int kx, int ky, float ar, float ai, float br, float bi) {
-        out[(long long)kx * p.ny + ky] = make_float2(ar - bi, ai + br);
+        out[kx * p.ny + ky] = make_float2(ar - bi, ai + br);      // nx*ny < 2^31
     };
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -304,7 +318,7 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
             float A[4], B[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                A[q] = stash[((i * 2 + k) * 4 + q) * 256 + tid];
+                A[q] = first[i][k][q];
                 B[q] = tot[i][k][q];
             }
             const float acc_ = A[0], ass = A[1], acs = A[2], asc = A[3];
@@ -341,22 +355,44 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
 std::mutex g_ws_mu;
 void* g_ws = nullptr;
 size_t g_ws_bytes = 0;
+void* g_ff4 = nullptr;         // gathered form factors of the current psb_build_transmission call
+size_t g_ff4_bytes = 0;
 
 }  // namespace
 
 void sf_fast_release() {
     std::lock_guard<std::mutex> lk(g_ws_mu);
     rt::dev_free(g_ws);
-    g_ws = nullptr;
-    g_ws_bytes = 0;
+    rt::dev_free(g_ff4);
+    g_ws = g_ff4 = nullptr;
+    g_ws_bytes = g_ff4_bytes = 0;
+}
+
+int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s) {
+    const size_t n = (size_t)ntypes * StructureFactorPaired::slots(nx) * StructureFactorPaired::slots(ny);
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    if (n * sizeof(float4) > g_ff4_bytes) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf workspace sync: ") + cudaGetErrorString(e));
+        rt::dev_free(g_ff4);
+        g_ff4 = rt::dev_alloc(n * sizeof(float4));
+        g_ff4_bytes = g_ff4 ? n * sizeof(float4) : 0;
+        if (!g_ff4) return PSB_ERR_NOMEM;
+    }
+    const long long blocks = (long long)((n + 255) / 256);
+    ff4_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, s>>>(ff, reinterpret_cast<float4*>(g_ff4), ntypes, nx, ny);
+    ++launch_counter();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("ff4 launch: ") + cudaGetErrorString(e));
+    return PSB_OK;
 }
 
 int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
-                   int ny, int pair_begin, int pair_count, int nf, const float* ff, float2* out, cudaStream_t s) {
+                   int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s) {
     SfFastParams p;
     std::memset(&p, 0, sizeof(p));
     p.offsets = offsets; p.ux = ux; p.uy = uy; p.cap = cap; p.nz = nz; p.ntypes = ntypes; p.nx = nx; p.ny = ny;
-    p.pair_begin = pair_begin; p.pair_count = pair_count; p.ff = ff; p.out = out;
+    p.pair_begin = pair_begin; p.pair_count = pair_count; p.out = out;
     p.tiles_x = (StructureFactorPaired::slots(nx) + TX - 1) / TX;
     p.tiles_y = (StructureFactorPaired::slots(ny) + TY - 1) / TY;
     const size_t nx_elems = (size_t)nf * p.tiles_x * cap * TX, ny_elems = (size_t)nf * p.tiles_y * cap * TY;
@@ -372,6 +408,8 @@ int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned in
             g_ws_bytes = g_ws ? need : 0;
             if (!g_ws) return PSB_ERR_NOMEM;
         }
+        if (!g_ff4) return fail(PSB_ERR_INVALID, "launch_sf_fast without sf_fast_prepare");
+        p.ff4 = reinterpret_cast<const float4*>(g_ff4);
         p.tabx = reinterpret_cast<float2*>(g_ws);
         p.taby = p.tabx + nx_elems;
         p.snx = reinterpret_cast<float*>(p.taby + ny_elems);

@@ -55,7 +55,12 @@ void run_line(const float2* in, float2* out, int reps) {
             fast::cpx v[16];
             for (int e = 0; e < 16; ++e) v[e] = in[j + e * T];
             HostXchg x{xa.data(), xb.data(), &bar};
-            for (int r = 0; r < reps; ++r) fast::line_fft<N, DIR>(v, tw, j, x, r * fast::exchanges<N>());
+            for (int r = 0; r < reps; ++r) {
+                fast::cpx w[16];
+                fast::line_fft<N, DIR>([&](int e) { return v[e]; }, [&](int e, fast::cpx a) { w[e] = a; }, tw, j, x,
+                                       r * fast::exchanges<N>());
+                for (int e = 0; e < 16; ++e) v[e] = w[e];
+            }
             for (int e = 0; e < 16; ++e) out[j + e * T] = v[e];
         });
     for (auto& t : th) t.join();
