@@ -276,7 +276,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "grid": [nx, ny, nz], "atoms": A, "frames_per_gpu": F,
                        "frames_total": T_total, "probes": 1, "voltage_eV": VOLTAGE,
-                       "l2": "inputs larger than L2 (transmission stack >= 24 GB per batch); no explicit flush",
+                       "l2": "inputs larger than L2: every timed step streams the positions and a >= 30 GB transmission stack per "
+                             "frame batch through HBM; only the psi batch (<= 80 MB) is L2-resident by design; no explicit flush",
+                       "frames_per_batch": engine.batch_sizes(calc._plan, 1, F)[0],
                        "tacaw_wall_ms": ms_dev / args.steps, "parallelism": f"frames sharded over {world} GPU(s), all-to-all to kx rows"},
             "e2e": {"value": e2e_value, "unit": "slice-steps/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": int(F * A * 3 * 8), "d2h_bytes_per_step": int(T_total * rows * ny * 4),
@@ -285,11 +287,12 @@ def main():
             "clocks": clocks,
             "phases_ms_per_step": {"potential": pot_ms / args.steps, "propagate_incl_exit_fft": prop_ms / args.steps,
                                    "other_incl_tacaw": (ms_dev - pot_ms - prop_ms) / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "slice-step = row pass + column pass (psb_propagate)",
+            "roofline": {"bound": "hbm", "kernel": "slice-step = fast_rows_kernel<256,0> + fast_cols_kernel<256,256,0> (psb_propagate)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes_per_slice_step": b_ss},
+                         "algorithmic_bytes_per_slice_step": b_ss,
+                         "traffic_note": "ncu dram bytes per launch pair (row + column pass, cold L2 under ncu), see profiles/roofline_traffic.json"},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
