@@ -62,6 +62,7 @@ void psb_release_tables(void) {
     free_all_tables();
 #ifndef PSB_EMU
     sf_fast_release();
+    sf_cols_release();
 #endif
 }
 long long psb_launch_count(void) { return launch_counter(); }
@@ -163,6 +164,17 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
             groups = (nm + sp.pairs_per_block - 1) / sp.pairs_per_block;
             int rc;
 #ifndef PSB_EMU
+            if (fast_path_enabled() && sf_cols_supported(nx, ny, nf * nm)) {
+                // structure factor + inverse column transform in one persistent kernel (sf_cols.cu), then the
+                // inverse row transform with the transmission epilogue
+                rc = launch_sf_cols(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, sf_fast_ff4(), f2(scratch), s);
+                if (rc != PSB_OK) return rc;
+                rc = launch_fast_rows_transmit(f2(scratch), nf * nm, nx, ny, scale / ((float)nx * (float)ny), sigma,
+                                               f2(t_out) + (long long)f0 * nz * img,
+                                               v_out ? v_out + (long long)f0 * nz * img : nullptr, nm, nz, mb, s);
+                if (rc != PSB_OK) return rc;
+                continue;
+            }
             if (fast_path_enabled())
                 rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, f2(scratch), s);
             else

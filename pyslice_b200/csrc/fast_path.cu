@@ -95,48 +95,25 @@ __device__ __forceinline__ void tensor2d_g2s(void* dst, const CUtensorMap* map, 
 }
 
 // exp(i*x) for the two halves of a packed pair at once (the transmission epilogue: two slices share one pixel of
-// the paired inverse transform).  Cody-Waite reduction by pi/2 in two steps and the degree-7 / degree-8 minimax
-// polynomials on [-pi/4, pi/4], evaluated with packed FMAs; measured max abs error 8.3e-8 for |x| <= 40 against
-// float64 (tools/diag notes in DESIGN.md).  |x| >= 256 takes libdevice's sincosf (never seen: x = sigma*V ~ a few rad).
-__device__ __noinline__ void pair_cis_slow(float xa, float xb, float* out4) {      // kept out of line: 32 inlined
-    float s, c;                                                                     // copies of libdevice's slow path
-    sincosf(xa, &s, &c);                                                            // would not fit the I-cache
-    out4[0] = c; out4[1] = s;
-    sincosf(xb, &s, &c);
-    out4[2] = c; out4[3] = s;
-}
+// the paired inverse transform).  Packed Cody-Waite reduction by whole turns (k = rint(x / 2 pi) through the
+// magic-number add, r = x - k*2pi in two FMAs), then the SFU: sin.approx / cos.approx on r in [-pi, pi], where
+// their absolute error is bounded by 2^-21.2 (4.2e-7).  The SFU pipe is otherwise idle in this kernel; the
+// degree-7/8 polynomial + quadrant selection this replaces cost ~60 FMA/ALU-pipe instructions per pixel pair and
+// made the epilogue more expensive than the transform (ncu r1h: issue-bound at 62 %, 33 us against a 22 us HBM
+// write floor).  Error budget: uniform noise of that half-width injected into every t of a 512-slice stack moves
+// the exit wave by 7.8e-6 rel-L2 and the TACAW cube by 1.0e-5 (tolerances 1e-4 / 1e-3; /tmp experiment recorded in
+// DESIGN.md section 4.2).
 __device__ __forceinline__ void pair_cis(cpx x, cpx& ea, cpx& eb) {
-    const float xa = fast::c_re(x), xb = fast::c_im(x);
-    if (fabsf(xa) >= 256.f || fabsf(xb) >= 256.f) {
-        float o[4];
-        pair_cis_slow(xa, xb, o);
-        ea = fast::c_make(o[0], o[1]);
-        eb = fast::c_make(o[2], o[3]);
-        return;
-    }
-    const float ka = rintf(xa * 0.63661977236758134f), kb = rintf(xb * 0.63661977236758134f);
-    const cpx k = fast::c_make(ka, kb);
-    cpx r = fast::fma2(k, fast::c_make(-1.5707963705062866f, -1.5707963705062866f), x);
-    r = fast::fma2(k, fast::c_make(4.371139000186241e-8f, 4.371139000186241e-8f), r);
-    const cpx s2 = fast::mul2(r, r);
-    cpx ps = fast::fma2(fast::c_make(-1.95152959e-4f, -1.95152959e-4f), s2, fast::c_make(8.33216087e-3f, 8.33216087e-3f));
-    ps = fast::fma2(ps, s2, fast::c_make(-1.66666546e-1f, -1.66666546e-1f));
-    ps = fast::mul2(ps, s2);
-    const cpx sn = fast::fma2(ps, r, r);
-    cpx pc = fast::fma2(fast::c_make(2.44331571e-5f, 2.44331571e-5f), s2, fast::c_make(-1.38873163e-3f, -1.38873163e-3f));
-    pc = fast::fma2(pc, s2, fast::c_make(4.16666457e-2f, 4.16666457e-2f));
-    pc = fast::fma2(pc, s2, fast::c_make(-0.5f, -0.5f));
-    const cpx cs = fast::fma2(pc, s2, fast::c_make(1.f, 1.f));
-    auto quadrant = [](float sn_, float cs_, float kf, cpx& out) {
-        const int q = __float2int_rn(kf);
-        float so = (q & 1) ? cs_ : sn_;
-        float co = (q & 1) ? sn_ : cs_;
-        if (q & 2) so = -so;
-        if ((q + 1) & 2) co = -co;
-        out = fast::c_make(co, so);
-    };
-    quadrant(fast::c_re(sn), fast::c_re(cs), ka, ea);
-    quadrant(fast::c_im(sn), fast::c_im(cs), kb, eb);
+    const cpx magic = fast::c_make(12582912.f, 12582912.f);                         // 1.5 * 2^23
+    cpx k = fast::fma2(x, fast::c_make(0.15915494309189535f, 0.15915494309189535f), magic);
+    k = fast::sub2(k, magic);
+    cpx r = fast::fma2(k, fast::c_make(-6.2831854820251465f, -6.2831854820251465f), x);
+    r = fast::fma2(k, fast::c_make(1.7484555e-7f, 1.7484555e-7f), r);               // 2 pi = 6.28318548... - 1.7484555e-7
+    float sa, ca, sb, cb;
+    __sincosf(fast::c_re(r), &sa, &ca);
+    __sincosf(fast::c_im(r), &sb, &cb);
+    ea = fast::c_make(ca, sa);
+    eb = fast::c_make(cb, sb);
 }
 
 // ---- row pass ------------------------------------------------------------------------------------------
@@ -217,17 +194,26 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
     const int upi_shift = 31 - __clz(p.nx / C::LPW);          // log2(units per image)
     const int upi_mask = (1 << upi_shift) - 1;
 
+    auto t_rows = [&](int unit) {
+        const unsigned img = (unsigned)unit >> upi_shift;
+        const int row0 = (unit & upi_mask) * C::LPW;
+        return p.t + (long long)(img / (unsigned)p.probes) * p.t_frame_stride + row0 * N;
+    };
     auto issue = [&](int unit, bool want_psi, bool want_t) {
         if (want_psi) {
             mbar_expect_tx(mb_psi, C::kBytes);
-            bulk_g2s(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi);
+#ifdef PSB_NO_EVICT
+            if (false)
+#else
+            if (MODE == R_TRANSMIT)      // last use of the chunk's rows: do not let them displace the next chunk's
+#endif
+                bulk_g2s_hint(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi, stream_once);
+            else
+                bulk_g2s(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi);
         }
         if (MODE == R_STEP && want_t) {
-            const unsigned img = (unsigned)unit >> upi_shift;
-            const int row0 = (unit & upi_mask) * C::LPW;
-            const float2* src = p.t + (long long)(img / (unsigned)p.probes) * p.t_frame_stride + row0 * N;
             mbar_expect_tx(mb_t, C::kBytes);
-            bulk_g2s_hint(land_t, src, C::kBytes, mb_t, stream_once);
+            bulk_g2s_hint(land_t, t_rows(unit), C::kBytes, mb_t, stream_once);
         }
     };
     if (u < n_units && lane == 0) issue(u, true, true);
@@ -274,11 +260,15 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
                     const cpx V2 = fast::mul2(a, scale2);         // (V_2m, V_2m+1)
                     cpx ta, tb;
                     pair_cis(fast::mul2(V2, sigma2), ta, tb);
-                    ta_out[e * C::T] = ta;
-                    if (p.v_out) p.v_out[o + e * C::T] = fast::c_re(V2);
+                    // streaming stores: t (134 MB per 64 MB chunk of spectra) must not evict the L2-resident chunk
+#ifdef PSB_NO_STCS
+#define __stcs(ptr, val) (*(ptr) = (val))
+#endif
+                    __stcs(ta_out + e * C::T, ta);
+                    if (p.v_out) __stcs(p.v_out + o + e * C::T, fast::c_re(V2));
                     if (has_b) {
-                        ta_out[img_elems + e * C::T] = tb;
-                        if (p.v_out) p.v_out[o + img_elems + e * C::T] = fast::c_im(V2);
+                        __stcs(ta_out + img_elems + e * C::T, tb);
+                        if (p.v_out) __stcs(p.v_out + o + img_elems + e * C::T, fast::c_im(V2));
                     }
                 },
                 tw, j, xc, 0,
@@ -505,8 +495,9 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const fl
 
 }  // namespace
 
-void fast_path_enable(int on) { g_fast_enabled.store(on ? 1 : 0); }
+void fast_path_enable(int level) { g_fast_enabled.store(level < 0 ? 0 : (level > 2 ? 2 : level)); }
 bool fast_path_enabled() { return g_fast_enabled.load() != 0; }
+int fast_path_level() { return g_fast_enabled.load(); }
 
 bool fast_slice_supported(int nx, int ny) {
     if (!g_fast_enabled.load()) return false;

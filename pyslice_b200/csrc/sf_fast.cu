@@ -368,6 +368,11 @@ void sf_fast_release() {
     g_ws_bytes = g_ff4_bytes = 0;
 }
 
+const float4* sf_fast_ff4() {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    return reinterpret_cast<const float4*>(g_ff4);
+}
+
 int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s) {
     const size_t n = (size_t)ntypes * StructureFactorPaired::slots(nx) * StructureFactorPaired::slots(ny);
     std::lock_guard<std::mutex> lk(g_ws_mu);

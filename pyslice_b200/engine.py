@@ -79,10 +79,12 @@ def launch_count() -> int:
     return int(_lib.lib().psb_launch_count())
 
 
-def set_fast_path(enable: bool) -> None:
-    """Diagnostic switch: route the steady-state slice step through the fused persistent kernels (default) or
-    through the generic line-pass kernels.  Both are CUDA; used by A/B parity tests and microbenchmarks."""
-    _lib.lib().psb_set_fast_path(1 if enable else 0)
+def set_fast_path(enable) -> None:
+    """Diagnostic switch between the kernel generations (all CUDA; used by A/B parity tests and microbenchmarks):
+    True / 1 = fused persistent kernels (default), 2 = experimental: structure factor fused with the inverse column
+    transform (sf_cols.cu), False / 0 = generic line-pass kernels."""
+    level = 1 if enable is True else (0 if enable is False else int(enable))
+    _lib.lib().psb_set_fast_path(level)
 
 
 def _device(device=None) -> torch.device:
@@ -197,6 +199,14 @@ def bin_atoms(plan: SlicePlan, positions: torch.Tensor):
     return offsets, atom_list, ux, uy
 
 
+def chunk_images(plan: SlicePlan, n_frames: int) -> int:
+    """Slice-pair images per chunk of the potential build: as many as SCRATCH_BYTES holds.  (Rounding the count to
+    whole rounds of the persistent grids -- 111 instead of 128 images at 256 x 256 on 148 SMs -- was measured and
+    lost: the third, small chunk per frame costs more than the structure-factor kernel's partial last round.)"""
+    img = plan.nx * plan.ny
+    return max(1, min(n_frames * ((plan.nz + 1) // 2), SCRATCH_BYTES // (8 * img)))
+
+
 def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential: bool = False,
                        out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None):
     """positions (F, A, 3) float64 on device -> t (F, nz, nx, ny) complex64 [, V float32]."""
@@ -207,7 +217,7 @@ def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential:
     V = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev) if want_potential else None
     scale = 1.0 / (plan.dx ** 2 * plan.dy ** 2)
     img = plan.nx * plan.ny
-    n_scratch = img * max(1, min(F * ((plan.nz + 1) // 2), SCRATCH_BYTES // (8 * img)))
+    n_scratch = img * chunk_images(plan, F)
     if scratch is None or scratch.numel() < n_scratch:
         scratch = torch.empty((n_scratch,), dtype=torch.complex64, device=dev)
     L = _lib.lib()

@@ -315,34 +315,61 @@ def test_fused_slice_step_vs_generic_and_oracle(box, n_probes, aperture, grid):
             assert rel_l2(out[True][p, f], ref[p, f]) < 1e-4
 
 
-@pytest.mark.parametrize("box,n_atoms,types", [
-    ((25.55, 25.55, 9.3), 900, (6, 14, 31)),      # 256 x 256: pipelined structure factor + fused inverse transforms
-    ((51.15, 25.55, 3.2), 500, (14,)),            # 512 x 256
-    ((6.35, 6.35, 4.1), 200, (6, 14, 31)),        # 64 x 64: pipelined structure factor + generic transforms
-    ((4.75, 3.95, 3.2), 150, (5, 7)),             # 48 x 40 (odd half sizes, Bluestein transforms)
-    ((2.45, 2.45, 30.2), 2500, (14,)),            # 25 x 25 odd grid, ~40 atoms per slice and > 32 in many (multi-block segments)
+@pytest.mark.parametrize("box,n_atoms,types,n_frames", [
+    ((25.55, 25.55, 9.3), 900, (6, 14, 31), 3),   # 256 x 256, 19 slices (odd: last pair is half empty), 3 types
+    ((51.15, 25.55, 3.2), 500, (14,), 3),         # 512 x 256
+    ((25.55, 51.15, 2.2), 700, (5, 7), 2),        # 256 x 512
+    ((51.15, 51.15, 1.2), 400, (6,), 2),          # 512 x 512
+    ((25.55, 25.55, 1.6), 6000, (14, 79), 2),     # 256 x 256, ~1500 atoms per slice: segments of many ring blocks
+    ((25.55, 25.55, 40.3), 300, (6, 14), 4),      # 256 x 256, 81 slices, ~2 atoms per (slice, type): empty segments
+    ((6.35, 6.35, 4.1), 200, (6, 14, 31), 3),     # 64 x 64: pipelined structure factor + generic transforms
+    ((4.75, 3.95, 3.2), 150, (5, 7), 3),          # 48 x 40 (odd half sizes, Bluestein transforms)
+    ((2.45, 2.45, 30.2), 2500, (14,), 3),         # 25 x 25 odd grid, ~40 atoms per slice and > 32 in many (multi-block segments)
 ])
-def test_potential_pipelined_vs_generic_and_oracle(box, n_atoms, types):
-    """psb_build_transmission through the pipelined structure-factor kernels (sf_fast.cu) and the fused
-    inverse transforms against the generic kernels (same inputs) and the oracle's potential."""
+def test_potential_pipelined_vs_generic_and_oracle(box, n_atoms, types, n_frames):
+    """psb_build_transmission through the three kernel generations -- 2: structure factor fused with the inverse
+    column transform (sf_cols.cu), 1: pipelined structure factor (sf_fast.cu) + stand-alone column pass, 0: generic
+    kernels -- on the same inputs, and against the oracle's potential."""
     from pyslice_b200 import engine, hostmath, synthetic
-    traj = synthetic.random_trajectory(n_atoms=n_atoms, box=box, n_frames=3, seed=13, types=types, stray=True)
+    traj = synthetic.random_trajectory(n_atoms=n_atoms, box=box, n_frames=n_frames, seed=13, types=types, stray=True)
     xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
     plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
     pos = dev(traj.positions)
     out = {}
-    for fast in (True, False):
-        engine.set_fast_path(fast)
+    for level in (2, 1, 0):
+        engine.set_fast_path(level)
         try:
             t, V = engine.build_transmission(plan, pos, want_potential=True)
-            out[fast] = (t.cpu().numpy(), V.cpu().numpy())
+            out[level] = (t.cpu().numpy(), V.cpu().numpy())
         finally:
             engine.set_fast_path(True)
-    assert rel_l2(out[True][1], out[False][1]) < 2e-6
-    assert rel_l2(out[True][0], out[False][0]) < 2e-6
+    for level in (2, 1):
+        assert rel_l2(out[level][1], out[0][1]) < 2e-6, level
+        assert rel_l2(out[level][0], out[0][0]) < 2e-6, level
     Vref = orc.potential(xs, ys, zs, traj.positions[1], traj.atom_types)      # (nx, ny, nz)
-    assert rel_l2(np.moveaxis(out[True][1][1], 0, 2), Vref) < 1e-5
-    assert np.allclose(np.abs(out[True][0]), 1.0, atol=1e-6)
+    for level in (2, 1):
+        err = rel_l2(np.moveaxis(out[level][1][1], 0, 2), Vref)
+        print(f"potential rel-L2 vs oracle, level {level}: {err:.3e}")
+        assert err < 1e-5, level
+    assert np.allclose(np.abs(out[2][0]), 1.0, atol=1e-6)
+
+
+def test_potential_small_scratch_chunks():
+    """chunks smaller than a frame's pair count (several launches per frame, partial last chunk) through the fused
+    structure-factor + column kernel equal the one-chunk result"""
+    from pyslice_b200 import engine, hostmath, synthetic
+    traj = synthetic.random_trajectory(n_atoms=800, box=(25.55, 25.55, 12.3), n_frames=2, seed=21, types=(6, 14), stray=True)
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    pos = dev(traj.positions)
+    t_ref = engine.build_transmission(plan, pos)
+    keep = engine.SCRATCH_BYTES
+    try:
+        engine.SCRATCH_BYTES = 5 * 256 * 256 * 8          # 5 pair images per chunk; 25 slices = 13 pairs per frame
+        t_small = engine.build_transmission(plan, pos)
+    finally:
+        engine.SCRATCH_BYTES = keep
+    assert torch.equal(t_ref, t_small)
 
 
 def test_fused_slice_step_many_images_ragged():

@@ -3,7 +3,10 @@ usage: python tools/microbench_potential.py [frames] [scratch_MB ...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
-from pyslice_b200 import engine, hostmath, synthetic
+from pyslice_b200 import engine, hostmath, synthetic, _lib
+if os.environ.get("PSB_VARIANT_LIB"):          # tuning experiments: time an alternative build of libpsb
+    _lib._lib = _lib.load(os.path.abspath(os.environ["PSB_VARIANT_LIB"]))
+    print("variant library:", os.environ["PSB_VARIANT_LIB"])
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 sizes = [int(x) for x in sys.argv[2:]] or [32, 64, 96]
@@ -13,7 +16,7 @@ plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
 pos = torch.from_numpy(traj.positions).cuda()
 tbuf = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device="cuda")
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for fast in (True, False):
+for fast in [int(x) for x in os.environ.get('PSB_LEVELS', '2,1,0').split(',')]:
     engine.set_fast_path(fast)
     for mb in sizes:
         engine.SCRATCH_BYTES = mb << 20
@@ -25,7 +28,7 @@ for fast in (True, False):
             engine.build_transmission(plan, pos, out=tbuf)
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 3
-        print(f"{'fused  ' if fast else 'generic'} scratch {mb:4d} MB  F={F}: {ms:8.3f} ms  {1e3*ms/(F*plan.nz):6.3f} us per slice  "
+        print(f"{'level %d' % fast} scratch {mb:4d} MB  F={F}: {ms:8.3f} ms  {1e3*ms/(F*plan.nz):6.3f} us per slice  "
               f"({F*plan.nz/ms/1e3:6.3f} M slices/s)", flush=True)
     # binning alone
     for _ in range(2):
