@@ -151,6 +151,7 @@ PSB_D void radix16_io(const In& in, const Out& out) {
 // ---- per-thread persistent twiddles ---------------------------------------------------------------
 // N = 256 (radix 16 x 16):       w[t-1] = exp(-2*pi*i*j*t/256),  t = 1..15
 // N = 512 (radix 16 x 2 x 16):   w[t-1] = exp(-2*pi*i*j*t/512),  w2 = exp(-2*pi*i*(j & 15)/32)
+//                                (the radix-2 stage is folded into the last stage's loads, see line_fft)
 template <int N>
 struct Twiddles {
     cpx w[15];
@@ -171,7 +172,6 @@ struct Twiddles {
     }
 };
 
-template <int N> constexpr int xi0_last() { return N == 512 ? 1 : 0; }
 
 // ---- the line transform -----------------------------------------------------------------------------
 // Xchg policy:  cpx* buf(int i)         exchange buffer of the i-th exchange of the current tile
@@ -199,44 +199,45 @@ PSB_D void line_fft(const In& in, const Out& out, const Twiddles<N>& tw, int j, 
         x.after_store(xi0);
         hook();
     }
-    if constexpr (N == 512) {
-        // stage 2: radix 2, NS = 16: butterfly m pairs positions b, b + 256 (b = j + 32*m), twiddle
-        // exp(-+2*pi*i*(b & 15)/32) = w2, outputs to (b/16)*32 + (b & 15) + u*16
-        // (all 16 loads complete before the first store: the two exchanges may share one buffer)
-        const cpx* s1 = x.buf(xi0);
-        cpx* s2 = x.buf(xi0 + 1);
-        cpx v[16];
-#pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = s1[x.at(j + e * T)];
-        x.after_load(xi0);
-#pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            cpx a0 = v[m];
-            cpx a1 = DIR < 0 ? cmulp(v[m + 8], tw.w2) : cmulcp(v[m + 8], tw.w2);
-            radix2<DIR>(a0, a1);
-            const int b = j + 32 * m;
-            const int q0 = (b >> 4) * 32 + (b & 15);
-            s2[x.at(q0)] = a0;
-            s2[x.at(q0 + 16)] = a1;
-        }
-        x.after_store(xi0 + 1);
-    }
     // last stage: radix 16 with the thread's own twiddles; outputs come out in natural strided order
-    constexpr int xl = xi0_last<N>();
-    const cpx* sl = x.buf(xi0 + xl);
+    const cpx* sl = x.buf(xi0);
     before_last();
-    radix16_io<DIR>(
-        [&](int t) {
-            const cpx a = sl[x.at(j + t * T)];
-            if (t == 0) return a;
-            return DIR < 0 ? cmulp(a, tw.w[t > 0 ? t - 1 : 0]) : cmulcp(a, tw.w[t > 0 ? t - 1 : 0]);
-        },
-        out);
-    x.after_load(xi0 + xl);
+    if constexpr (N == 512) {
+        // The radix-2 stage (NS = 16: butterfly pairs positions b and b + 256, twiddle exp(-+2*pi*i*(b & 15)/32) = w2)
+        // is folded into the loads of the last stage instead of taking its own trip through shared memory: its
+        // outputs land at (b/16)*32 + (b & 15) [sum] and + 16 [difference], and the last stage wants positions
+        // j + 32*t of that array -- for j < 16 those are the sums of b = 16*t + j, for j >= 16 the differences of
+        // b = 16*t + (j - 16).  So thread j loads both butterfly inputs itself and keeps one output; the partner
+        // thread j ^ 16 loads the same two words (a broadcast) and keeps the other.  32 loads instead of
+        // 16 loads + 16 stores + 16 loads, one exchange and one barrier less per transform, 8 extra complex
+        // multiplies per thread.
+        const int jj = j & 15;
+        const float sg = (j & 16) ? -1.f : 1.f;
+        const cpx sg2 = c_make(sg, sg);
+        radix16_io<DIR>(
+            [&](int t) {
+                const int b = 16 * t + jj;
+                const cpx lo = sl[x.at(b)], hi = sl[x.at(b + 256)];
+                const cpx hw = DIR < 0 ? cmulp(hi, tw.w2) : cmulcp(hi, tw.w2);
+                const cpx a = fma2(hw, sg2, lo);
+                if (t == 0) return a;
+                return DIR < 0 ? cmulp(a, tw.w[t > 0 ? t - 1 : 0]) : cmulcp(a, tw.w[t > 0 ? t - 1 : 0]);
+            },
+            out);
+    } else {
+        radix16_io<DIR>(
+            [&](int t) {
+                const cpx a = sl[x.at(j + t * T)];
+                if (t == 0) return a;
+                return DIR < 0 ? cmulp(a, tw.w[t > 0 ? t - 1 : 0]) : cmulcp(a, tw.w[t > 0 ? t - 1 : 0]);
+            },
+            out);
+    }
+    x.after_load(xi0);
 }
 
 // number of shared-memory exchanges of one line transform
-template <int N> constexpr int exchanges() { return N == 512 ? 2 : 1; }
+template <int N> constexpr int exchanges() { return 1; }
 
 }  // namespace fast
 }  // namespace psb

@@ -33,6 +33,7 @@ int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s)
 int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
                    int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s);
 void sf_fast_release();
+#ifndef PSB_EMU
 const float4* sf_fast_ff4();      // the table gathered by the last sf_fast_prepare
 
 // structure factor + inverse column transform of slice pairs [pair_begin, pair_begin + pair_count) of nf frames
@@ -41,5 +42,6 @@ bool sf_cols_supported(int nx, int ny, int n_img);
 int launch_sf_cols(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
                    int ny, int pair_begin, int pair_count, int nf, const float4* ff4, float2* out, cudaStream_t s);
 void sf_cols_release();
+#endif
 
 }  // namespace psb

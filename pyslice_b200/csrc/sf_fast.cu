@@ -166,6 +166,7 @@ __device__ __forceinline__ void iter_next(BlockIter& it, const int* off, int m, 
 }
 
 constexpr int kStageElems = CH * (TX + TY);
+constexpr int kMaxStagedTypes = 64;
 constexpr size_t kSfSmem = 2 * (size_t)kStageElems * sizeof(float2) + 2 * sizeof(uint64_t);
 
 // K2
@@ -180,7 +181,7 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
     const int ml = blockIdx.y, m = p.pair_begin + ml, fl = blockIdx.z;
     const int tid = threadIdx.x, tx = tid % 16, ty = tid / 16;
     const int nseg = p.nz * p.ntypes;
-    const int* off = p.offsets + (long long)fl * (nseg + 1);
+    const int* goff = p.offsets + (long long)fl * (nseg + 1);
     const bool nq_x = p.nx % 2 == 0, nq_y = p.ny % 2 == 0;
     const bool corner_tile = kx0 == 0 && ky0 == 0 && nq_x && nq_y;
     const float2* tabx = p.tabx + ((long long)fl * p.tiles_x + tile_x) * p.cap * TX;
@@ -194,8 +195,15 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
         mbar_init(&full[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();
     pdl_wait();          // offsets / tables come from the previous kernels of the chain
+    // the pair's segment offsets, staged once: the producer's block iterator and every thread's segment loop read
+    // them many times, and as global loads each of those reads was a dependent L2 round trip (ncu r1h: ~10 % of the
+    // kernel's stall samples)
+    __shared__ int soff[2 * kMaxStagedTypes + 1];          // launch_sf_fast rejects more types
+    const int obase = 2 * m * p.ntypes;
+    if (tid <= 2 * p.ntypes) soff[tid] = goff[obase + tid < nseg ? obase + tid : nseg];
+    const int* off = soff - obase;
+    __syncthreads();
 
     int gx[4], gy[2];
 #pragma unroll
@@ -398,6 +406,7 @@ int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned in
     std::memset(&p, 0, sizeof(p));
     p.offsets = offsets; p.ux = ux; p.uy = uy; p.cap = cap; p.nz = nz; p.ntypes = ntypes; p.nx = nx; p.ny = ny;
     p.pair_begin = pair_begin; p.pair_count = pair_count; p.out = out;
+    if (ntypes > kMaxStagedTypes) return fail(PSB_ERR_UNSUPPORTED, "pipelined structure factor: more than 64 atom types");
     p.tiles_x = (StructureFactorPaired::slots(nx) + TX - 1) / TX;
     p.tiles_y = (StructureFactorPaired::slots(ny) + TY - 1) / TY;
     const size_t nx_elems = (size_t)nf * p.tiles_x * cap * TX, ny_elems = (size_t)nf * p.tiles_y * cap * TY;
