@@ -42,9 +42,10 @@ int psb_sm_count(void);
 void psb_release_tables(void);
 /* kernels launched by this library in this process so far (benchmark bookkeeping) */
 long long psb_launch_count(void);
-/* diagnostic switch: 0 routes the steady-state slice step through the generic line-pass kernels instead of
- * the fused persistent kernels (both are CUDA; used by microbenchmarks and A/B parity tests). Default 1. */
-void psb_set_fast_path(int enable);
+/* diagnostic switch between kernel generations (all CUDA; used by microbenchmarks and A/B parity tests):
+ * 0 = generic line-pass kernels, 1 = fused persistent kernels (default), 2 = 1 plus the experimental
+ * structure-factor + column-transform fusion (csrc/sf_cols.cu, measured slower on B200). */
+void psb_set_fast_path(int level);
 
 /* ---- atom -> slice binning: src/multislice/potentials.py:297-317 (+ bounds :304-305) -------------
  * positions (F, A, 3) float64; type_idx (A) dense type index in [0, ntypes);

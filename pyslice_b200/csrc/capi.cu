@@ -66,11 +66,11 @@ void psb_release_tables(void) {
 #endif
 }
 long long psb_launch_count(void) { return launch_counter(); }
-void psb_set_fast_path(int enable) {
+void psb_set_fast_path(int level) {
 #ifndef PSB_EMU
-    fast_path_enable(enable);
+    fast_path_enable(level);
 #else
-    (void)enable;
+    (void)level;
 #endif
 }
 

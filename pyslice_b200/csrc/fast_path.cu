@@ -135,16 +135,25 @@ struct RowPassParams {
 
 enum RowMode { R_STEP = 0, R_TRANSMIT = 1 };
 
-template <int N>
+// transmission landing buffers per warp (R_STEP): with 2 the copy of unit n+2's rows is issued while unit n is
+// transformed, a full unit of lead more against the HBM round trip, at the price of 12 instead of 16 warps per SM
+#ifndef PSB_ROW_TBUFS
+#define PSB_ROW_TBUFS 1
+#endif
+
+template <int N, int MODE = 0>
 struct RowCfg {
     static constexpr int T = N / 16;               // threads per line
     static constexpr int LPW = 32 / T;             // lines per warp
     static constexpr int NP = N + N / 16;          // padded exchange pitch
-    static constexpr int kWarps = 16;
+    static constexpr int kTBufs = (MODE == 0) ? PSB_ROW_TBUFS : 1;
+    static constexpr int kWarps = (kTBufs == 1) ? 16 : 12;
+    static constexpr int kThreads = 32 * kWarps;
     static constexpr int kLand = LPW * N;          // float2 per landing buffer (4 KB)
     static constexpr int kX = LPW * NP;
-    static constexpr int kWarpElems = 2 * kLand + kX;
-    static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + kWarps * 2 * sizeof(uint64_t);
+    static constexpr int kWarpElems = (1 + kTBufs) * kLand + kX;
+    static constexpr int kBars = 1 + kTBufs;
+    static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + kWarps * kBars * sizeof(uint64_t);
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
 };
 
@@ -159,22 +168,22 @@ struct RowXchg {
 };
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p) {
-    using C = RowCfg<N>;
+__global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel(const RowPassParams p) {
+    using C = RowCfg<N, MODE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* sm = reinterpret_cast<cpx*>(smem_raw);
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: bulk copies take uniform operands
     const int lane = threadIdx.x & 31;
     cpx* land_psi = sm + (size_t)warp * C::kWarpElems;
-    cpx* land_t = land_psi + C::kLand;
-    cpx* xb = land_t + C::kLand;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)C::kWarps * C::kWarpElems) + 2 * warp;
+    cpx* land_t = land_psi + C::kLand;                       // [kTBufs][kLand]
+    cpx* xb = land_t + C::kTBufs * C::kLand;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)C::kWarps * C::kWarpElems) + C::kBars * warp;
     uint64_t* mb_psi = bars;
-    uint64_t* mb_t = bars + 1;
+    uint64_t* mb_t = bars + 1;                               // [kTBufs]
 
     if (lane == 0) {
-        mbar_init(mb_psi, 1);
-        mbar_init(mb_t, 1);
+#pragma unroll
+        for (int b = 0; b < C::kBars; ++b) mbar_init(bars + b, 1);
         mbar_init_fence();
     }
     pdl_trigger();
@@ -199,7 +208,7 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
         const int row0 = (unit & upi_mask) * C::LPW;
         return p.t + (long long)(img / (unsigned)p.probes) * p.t_frame_stride + row0 * N;
     };
-    auto issue = [&](int unit, bool want_psi, bool want_t) {
+    auto issue = [&](int unit, bool want_psi, bool want_t, int tb = 0) {
         if (want_psi) {
             mbar_expect_tx(mb_psi, C::kBytes);
 #ifdef PSB_NO_EVICT
@@ -212,22 +221,30 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
                 bulk_g2s(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi);
         }
         if (MODE == R_STEP && want_t) {
-            mbar_expect_tx(mb_t, C::kBytes);
-            bulk_g2s_hint(land_t, t_rows(unit), C::kBytes, mb_t, stream_once);
+            mbar_expect_tx(mb_t + tb, C::kBytes);
+            bulk_g2s_hint(land_t + tb * C::kLand, t_rows(unit), C::kBytes, mb_t + tb, stream_once);
         }
     };
-    if (u < n_units && lane == 0) issue(u, true, true);
+    if (u < n_units && lane == 0) {
+        issue(u, true, true, 0);
+#pragma unroll
+        for (int b = 1; b < C::kTBufs; ++b)
+            if (u + b * GW < n_units) issue(u + b * GW, false, true, b);
+    }
 
     for (uint32_t it = 0; u < n_units; u += GW, ++it) {
         const uint32_t parity = it & 1u;
         const int un = u + GW;
         const bool next = un < n_units;
+        const int tb = (int)(it % C::kTBufs);                        // this unit's transmission buffer
+        const uint32_t t_parity = (it / C::kTBufs) & 1u;
+        const int ut = u + C::kTBufs * GW;                           // the unit whose rows refill it
         mbar_wait(mb_psi, parity);
         // The landing buffers go back to the async proxy only from inside the transforms, after the first
         // exchange: its stores depend on every value loaded from them, so those loads have completed by then.
         // (Issuing right after a __syncwarp let the next unit's TMA overwrite words whose LDS was still in flight.)
         const cpx* lp = land_psi + c * N + j;
-        const cpx* lt = land_t + c * N + j;
+        const cpx* lt = land_t + tb * C::kLand + c * N + j;
         if constexpr (MODE == R_STEP) {
             cpx v[16];
             // psi[x, ky] -> IFFT_y -> * t[x, y]
@@ -237,11 +254,11 @@ __global__ void __launch_bounds__(512, 1) fast_rows_kernel(const RowPassParams p
                 [&]() {
                     if (lane == 0 && next) issue(un, true, false);
                 },
-                [&]() { mbar_wait(mb_t, parity); });
+                [&]() { mbar_wait(mb_t + tb, t_parity); });
             // -> FFT_y -> global
             cpx* dst = reinterpret_cast<cpx*>(p.psi) + (long long)u * C::kLand + c * N + j;
             fast::line_fft<N, -1>([&](int e) { return v[e]; }, [&](int e, cpx a) { dst[e * C::T] = a; }, tw, j, xc, 0, [&]() {
-                if (lane == 0 && next) issue(un, false, true);
+                if (lane == 0 && ut < n_units) issue(ut, false, true, tb);
             });
         } else {
             // potentials.py:336-342 + multislice.py:281-282: V = Re/Im(IFFT2) * scale, t = exp(i*sigma*V), two slices per image
@@ -447,7 +464,7 @@ int encode_cols_map(CUtensorMap* map, float2* psi, long long rows_total, int ny,
 
 template <int N, int MODE>
 int rows_go(const RowPassParams& p, cudaStream_t s) {
-    using C = RowCfg<N>;
+    using C = RowCfg<N, MODE>;
     static bool ready = false;
     if (!ready) {
         int rc = ensure_smem(fast_rows_kernel<N, MODE>, C::kSmem, "fast row pass");
@@ -457,7 +474,7 @@ int rows_go(const RowPassParams& p, cudaStream_t s) {
     long long want = (p.n_units + C::kWarps - 1) / C::kWarps;
     const int sms = rt::sm_count();
     const int grid = (int)(want < sms ? want : sms);
-    cudaError_t e = pdl_launch(fast_rows_kernel<N, MODE>, dim3(grid), dim3(512), C::kSmem, s, p);
+    cudaError_t e = pdl_launch(fast_rows_kernel<N, MODE>, dim3(grid), dim3(C::kThreads), C::kSmem, s, p);
     ++launch_counter();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast row pass launch: ") + cudaGetErrorString(e));
     return PSB_OK;
