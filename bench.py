@@ -47,7 +47,17 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
+
+    def wait_ready(self, timeout=8.0):
+        """block until nvidia-smi delivered its first sample (its start-up is over)"""
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.05)
+
+    def mark(self):
+        """the timed region starts here: earlier samples (warm-up) are not reported"""
+        self.first = len(self.rows)
 
     def start(self):
         try:
@@ -73,7 +83,7 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -198,12 +208,17 @@ def main():
         tac = TACAWData(wf)
         return tac
 
-    for _ in range(args.warmup):
-        device_step()
-    barrier()
+    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, device enumeration) takes driver
+    # locks that stall kernel launches for tens of milliseconds when it lands inside the timed region; only the
+    # samples taken during the timed region are reported
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_ready()
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler.mark()
     l0 = engine.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

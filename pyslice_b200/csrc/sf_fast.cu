@@ -10,7 +10,7 @@
 //                     reduction, laid out [tile][entry][slot-in-tile] so that the rows a tile needs for one
 //                     (slice, type) segment are ONE contiguous block;
 //   K2  SfTiles       one CTA per (64 x 32 slot tile, slice pair, frame): the blocks of up to 32 atoms stream
-//                     global -> shared with cp.async.bulk through a 2-stage mbarrier ring while the previous
+//                     global -> shared with cp.async.bulk through a 2-stage mbarrier ring (deeper rings measured: no gain) while the previous
 //                     block is accumulated with FFMA2 (a thread owns 4 x 2 slots x 4 sums = 16 packed
 //                     accumulators); form factor, pairing and the mirror expansion as before.
 //
@@ -167,13 +167,21 @@ __device__ __forceinline__ void iter_next(BlockIter& it, const int* off, int m, 
 
 constexpr int kStageElems = CH * (TX + TY);
 constexpr int kMaxStagedTypes = 64;
-constexpr size_t kSfSmem = 2 * (size_t)kStageElems * sizeof(float2) + 2 * sizeof(uint64_t);
+#ifndef PSB_SF_STAGES
+#define PSB_SF_STAGES 2
+#endif
+constexpr int kSfStages = PSB_SF_STAGES;      // blocks of atoms in flight per CTA (ring depth)
+constexpr size_t kSfSmem = kSfStages * (size_t)kStageElems * sizeof(float2) + kSfStages * sizeof(uint64_t) + 32 * 256 * sizeof(float);
 
 // K2
 __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    cpx* stage = reinterpret_cast<cpx*>(smem_raw);                         // [2][CH*TX + CH*TY]
-    uint64_t* full = reinterpret_cast<uint64_t*>(stage + 2 * kStageElems); // [2]
+    cpx* stage = reinterpret_cast<cpx*>(smem_raw);                                  // [kSfStages][CH*TX + CH*TY]
+    uint64_t* full = reinterpret_cast<uint64_t*>(stage + kSfStages * kStageElems);  // [kSfStages]
+    // totals of the pair's first slice wait here while the second one accumulates: as 32 more live registers they
+    // pushed the kernel to the 128-register cap and ptxas stopped hoisting the loop's loads over its FMAs (ncu r1i,
+    // C4 geometry: short-scoreboard stalls on every FFMA2 of that copy of the loop, 2.3x the time per atom)
+    float* stash = reinterpret_cast<float*>(full + kSfStages);                      // [32][256]
 
     const int nsx = StructureFactorPaired::slots(p.nx), nsy = StructureFactorPaired::slots(p.ny);
     const int tile_x = blockIdx.x / p.tiles_y, tile_y = blockIdx.x % p.tiles_y;
@@ -191,8 +199,8 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
 
     pdl_trigger();
     if (tid == 0) {
-        mbar_init(&full[0], 1);
-        mbar_init(&full[1], 1);
+#pragma unroll
+        for (int i = 0; i < kSfStages; ++i) mbar_init(&full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     pdl_wait();          // offsets / tables come from the previous kernels of the chain
@@ -211,7 +219,7 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
 #pragma unroll
     for (int k = 0; k < 2; ++k) gy[k] = ky0 + tx + 16 * k;
 
-    // producer side: thread 0 keeps two blocks in flight
+    // producer side: thread 0 keeps kSfStages blocks in flight
     BlockIter ahead{0, 0, 0, 0, false};
     iter_seek(ahead, off, m, p.nz, p.ntypes);
     int issued = 0;
@@ -219,8 +227,8 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
         if (!ahead.valid) return;
         if (tid == 0) {
             const int nc = ahead.e - ahead.c0 < CH ? ahead.e - ahead.c0 : CH;
-            cpx* dst = stage + (issued & 1) * kStageElems;
-            uint64_t* bar = &full[issued & 1];
+            cpx* dst = stage + (issued % kSfStages) * kStageElems;
+            uint64_t* bar = &full[issued % kSfStages];
             mbar_expect_tx(bar, (uint32_t)(nc * (TX + TY) * sizeof(float2)));
             bulk_g2s(dst, tabx + (long long)ahead.c0 * TX, (uint32_t)(nc * TX * sizeof(float2)), bar);
             bulk_g2s(dst + CH * TX, taby + (long long)ahead.c0 * TY, (uint32_t)(nc * TY * sizeof(float2)), bar);
@@ -228,12 +236,11 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
         ++issued;
         iter_next(ahead, off, m, p.nz, p.ntypes);
     };
-    issue();
-    issue();
+#pragma unroll 1
+    for (int i = 0; i < kSfStages; ++i) issue();
 
     int used = 0;
     float tot[4][2][4];     // [i][k][cc, ss, cs, sc], multiplied by the form factor
-    float first[4][2][4];   // the pair's first slice while the second one accumulates
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -258,9 +265,9 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
                     }
                 for (int c0 = b; c0 < e; c0 += CH) {
                     const int nc = e - c0 < CH ? e - c0 : CH;
-                    const cpx* ex = stage + (used & 1) * kStageElems;
+                    const cpx* ex = stage + (used % kSfStages) * kStageElems;
                     const cpx* ey = ex + CH * TX;
-                    mbar_wait(&full[used & 1], (uint32_t)((used >> 1) & 1));
+                    mbar_wait(&full[used % kSfStages], (uint32_t)((used / kSfStages) & 1));
 #pragma unroll 4
                     for (int a = 0; a < nc; ++a) {
                         cpx ys[2];
@@ -309,7 +316,7 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
 #pragma unroll
                 for (int k = 0; k < 2; ++k)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) first[i][k][q] = tot[i][k][q];
+                    for (int q = 0; q < 4; ++q) stash[((i * 2 + k) * 4 + q) * 256 + tid] = tot[i][k][q];
         }
     }
     // tot = second slice (B), first = first slice (A):  Z = S'_A + i*S'_B at up to four mirror positions
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
             float A[4], B[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                A[q] = first[i][k][q];
+                A[q] = stash[((i * 2 + k) * 4 + q) * 256 + tid];
                 B[q] = tot[i][k][q];
             }
             const float acc_ = A[0], ass = A[1], acs = A[2], asc = A[3];
