@@ -5,13 +5,19 @@ Differences from the reference that a caller can observe (all documented in DESI
   * results are complex64 CUDA tensors instead of complex128 CPU tensors;
   * frames are processed in batches on the GPU; with `torch.distributed` initialised (one process
     per GPU) each rank propagates a contiguous block of frames and `WFData.shard` records it;
-  * no `psi_data/` frame cache is written (the reference's cache key ignores atom positions);
+  * the `psi_data/torch_<key>/frame_<i>.npy` frame cache (reference calculators.py:81-92,140,259-260,311) is
+    opt-in (`frame_cache=`) instead of a side effect of every run, and its default key also covers the atom
+    positions (the reference's key ignores them, so a new trajectory of the same shape silently reads the old
+    frames); `cache_key="reference"` reproduces the reference's key to read caches it wrote;
   * new optional kwarg `layer_every`: also record the wave function after every n-th slice
     (layer axis of WFData); the default 0 reproduces the reference's single layer.
 """
 from __future__ import annotations
 
+import hashlib
 import logging
+import queue
+import threading
 import time
 from dataclasses import dataclass
 from pathlib import Path
@@ -59,6 +65,37 @@ def split_frames(n_frames: int, world: int) -> List[int]:
     return [n_frames // world + (1 if r < n_frames % world else 0) for r in range(world)]
 
 
+class _FrameWriter:
+    """Background writer of the per-frame cache files: (P, nx, ny) complex64 host tensors in, `.npy` files of shape
+    (P, nx, ny, 1, 1) complex128 out (the reference's wire format)."""
+
+    def __init__(self):
+        self.q = queue.Queue(maxsize=64)
+        self.err = None
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        while True:
+            item = self.q.get()
+            if item is None:
+                return
+            path, frame = item
+            try:
+                np.save(path, frame.numpy().astype(np.complex128)[:, :, :, None, None])
+            except Exception as e:          # surfaced by close()
+                self.err = e
+
+    def put(self, path, frame):
+        self.q.put((path, frame))
+
+    def close(self):
+        self.q.put(None)
+        self.th.join()
+        if self.err is not None:
+            raise self.err
+
+
 class MultisliceCalculator:
 
     def __init__(self, device=None, force_cpu=False):
@@ -85,10 +122,18 @@ class MultisliceCalculator:
         slice_axis: int = 2,
         layer_every: int = 0,
         shard_frames: Optional[bool] = None,
+        frame_cache=False,
+        cache_key: str = "positions",
     ):
         """Same keyword arguments and defaults as the reference (calculators.py:96-109).
         `defocus`, `batch_size`, `save_path`, `cleanup_temp_files` are accepted and, as in the
-        reference, have no effect on the result."""
+        reference, have no effect on the result.
+
+        frame_cache: False (default) / True (`./psi_data`, the reference's location) / a directory.  When on, every
+        frame's exit waves are written to `<dir>/torch_<key>/frame_<i>.npy` in the reference's wire format
+        ((P, nx, ny, 1, 1) complex128, calculators.py:276,311) by a writer thread, and frames whose file exists
+        are loaded instead of computed (calculators.py:259-260).  cache_key: "positions" (default: the reference's
+        parameters plus a digest of the positions) or "reference" (exactly calculators.py:81-92)."""
         if slice_axis != 2:
             raise NotImplementedError("pyslice_b200 supports slice_axis=2 only")
         self.trajectory = trajectory
@@ -102,6 +147,17 @@ class MultisliceCalculator:
         self.cleanup_temp_files = cleanup_temp_files
         self.slice_axis = slice_axis
         self.layer_every = int(layer_every)
+        if cache_key not in ("positions", "reference"):
+            raise ValueError("cache_key must be 'positions' or 'reference'")
+        if frame_cache and self.layer_every > 0:
+            raise ValueError("the frame cache holds exit waves only (reference format): not available with layer_every")
+        self.output_dir = None
+        if frame_cache:
+            key = self._generate_cache_key(trajectory, aperture, voltage_eV, slice_thickness, sampling, probe_positions,
+                                           with_positions=(cache_key == "positions"))
+            root = Path("psi_data") if frame_cache is True else Path(frame_cache)
+            self.output_dir = root / f"torch_{key}"
+            self.output_dir.mkdir(parents=True, exist_ok=True)
 
         xs, ys, zs, lx, ly, lz = gridFromTrajectory(trajectory, sampling=sampling, slice_thickness=slice_thickness)
         self.xs, self.ys, self.zs = xs, ys, zs
@@ -127,6 +183,31 @@ class MultisliceCalculator:
         self.wavefunction_data = None
 
     # -----------------------------------------------------------------------------------------
+    def _generate_cache_key(self, trajectory, aperture, voltage_eV, slice_thickness, sampling, probe_positions,
+                            with_positions: bool = False) -> str:
+        """The reference's key (calculators.py:78-92: md5 of the sorted parameter dict, 12 hex digits; 'backend'
+        is 'pytorch' as in a reference run with torch installed); `with_positions` appends a digest of the positions."""
+        params = {
+            'n_frames': trajectory.n_frames,
+            'n_atoms': trajectory.n_atoms,
+            'box_matrix': trajectory.box_matrix.tolist(),
+            'atom_types': trajectory.atom_types.tolist(),
+            'aperture': aperture,
+            'voltage_eV': voltage_eV,
+            'slice_thickness': slice_thickness,
+            'sampling': sampling,
+            'probe_positions': probe_positions,
+            'backend': 'pytorch',
+        }
+        if with_positions:
+            pos = trajectory.positions
+            pos = pos.detach().cpu().numpy() if isinstance(pos, torch.Tensor) else np.asarray(pos)
+            params['positions_sha1'] = hashlib.sha1(np.ascontiguousarray(pos, dtype=np.float64).tobytes()).hexdigest()
+        return hashlib.md5(str(sorted(params.items())).encode()).hexdigest()[:12]
+
+    def _cache_file(self, frame: int) -> Path:
+        return self.output_dir / f"frame_{frame}.npy"
+
     def _local_frames(self):
         if self.shard is None:
             return 0, self.n_frames
@@ -146,21 +227,60 @@ class MultisliceCalculator:
         work = torch.empty((fb * min(pb, P), nx, ny), dtype=torch.complex64, device=self.device)
         tbuf = torch.empty((fb, plan.nz, nx, ny), dtype=torch.complex64, device=self.device)
         positions = self.trajectory.positions
-        for b0 in range(0, T_loc, fb):
-            nb = min(fb, T_loc - b0)
-            block = positions[f_lo + b0:f_lo + b0 + nb]
-            if isinstance(block, torch.Tensor):      # already resident (device arm of bench.py)
-                pos_d = block.to(device=self.device, dtype=torch.float64).contiguous()
-            else:
-                pos = np.ascontiguousarray(block, dtype=np.float64)
-                pos_d = torch.from_numpy(pos).to(self.device, non_blocking=True)
-            with timer.phase("potential"):
-                t = engine.build_transmission(plan, pos_d, out=tbuf[:nb])
-            with timer.phase("propagate"):
-                for p0 in range(0, P, pb):
-                    np_ = min(pb, P - p0)
-                    engine.propagate(plan, self._probes[p0:p0 + np_], t, wf_out=store, frame0=b0, probe0=p0,
-                                     layer_every=self.layer_every, work=work)
+        # frame cache (opt-in): cached frames are loaded, the others are computed in contiguous runs and handed to
+        # a writer thread (D2H on a side stream would buy nothing here: the files are written by the host anyway)
+        cached = [False] * T_loc
+        writer = None
+        if self.output_dir is not None:
+            cached = [self._cache_file(f_lo + i).exists() for i in range(T_loc)]
+            for i in range(T_loc):
+                if cached[i]:
+                    data = np.load(self._cache_file(f_lo + i))            # (P, nx, ny, 1, 1), reference wire format
+                    if data.shape != (P, nx, ny, 1, 1):
+                        raise ValueError(f"{self._cache_file(f_lo + i)}: shape {data.shape}, expected {(P, nx, ny, 1, 1)}")
+                    store[0, :, i] = torch.from_numpy(np.ascontiguousarray(data[:, :, :, 0, 0])).to(self.device, torch.complex64)
+            writer = _FrameWriter()
+        self.frames_cached = sum(cached)
+        self.frames_computed = T_loc - self.frames_cached
+        runs, i = [], 0
+        while i < T_loc:                                  # contiguous runs of frames to compute
+            if cached[i]:
+                i += 1
+                continue
+            j = i
+            while j < T_loc and not cached[j]:
+                j += 1
+            runs.append((i, j))
+            i = j
+        for r0, r1 in runs:
+            for b0 in range(r0, r1, fb):
+                nb = min(fb, r1 - b0)
+                block = positions[f_lo + b0:f_lo + b0 + nb]
+                if isinstance(block, torch.Tensor):      # already resident (device arm of bench.py)
+                    pos_d = block.to(device=self.device, dtype=torch.float64).contiguous()
+                else:
+                    pos = np.ascontiguousarray(block, dtype=np.float64)
+                    pos_d = torch.from_numpy(pos).to(self.device, non_blocking=True)
+                with timer.phase("potential"):
+                    t = engine.build_transmission(plan, pos_d, out=tbuf[:nb])
+                with timer.phase("propagate"):
+                    for p0 in range(0, P, pb):
+                        np_ = min(pb, P - p0)
+                        engine.propagate(plan, self._probes[p0:p0 + np_], t, wf_out=store, frame0=b0, probe0=p0,
+                                         layer_every=self.layer_every, work=work)
+                if writer is not None:
+                    host = store[0, :, b0:b0 + nb].to("cpu")                 # (P, nb, nx, ny); synchronises this batch
+                    for k in range(nb):
+                        writer.put(self._cache_file(f_lo + b0 + k), host[:, k])
+        if writer is not None:
+            writer.close()
+            if self.cleanup_temp_files:                   # reference calculators.py:235-245
+                for i in range(T_loc):
+                    self._cache_file(f_lo + i).unlink(missing_ok=True)
+                try:
+                    self.output_dir.rmdir()
+                except OSError:
+                    pass
         # (L, P, T, nx, ny) storage exposed in the reference's (P, T, nx, ny, L) index order
         self.wavefunction_data = store.permute(1, 2, 3, 4, 0)
         logger.info(f"Simulation completed in {time.time() - t_start:.2f}s ({T_loc} frames computed)")
