@@ -412,3 +412,77 @@ def test_errors_are_loud():
     x = torch.zeros((1, 3, 9000), dtype=torch.complex64, device="cuda")
     with pytest.raises(_lib.PsbError):
         engine.fft2(x)                      # 9000 > 4096 and not a power of two -> unsupported
+
+
+def test_frame_cache_on_device(tmp_path):
+    """SURVEY 8f-3 on the CUDA path: files in the reference's wire format, reload equals the computed run"""
+    from pyslice_b200 import synthetic
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    traj = synthetic.random_trajectory(n_atoms=120, box=(6.35, 6.35, 3.1), n_frames=5, seed=4, types=(6, 14))
+    pp = [(1.0, 2.0), (4.0, 5.0), (3.0, 3.0)]
+    c = MultisliceCalculator()
+    c.setup(traj, aperture=20.0, voltage_eV=100e3, probe_positions=pp, frame_cache=tmp_path)
+    wf = c.run().wavefunction_data.clone()
+    assert (c.frames_computed, c.frames_cached) == (5, 0)
+    a = np.load(c.output_dir / "frame_3.npy")
+    assert a.shape == (3, 64, 64, 1, 1) and a.dtype == np.complex128
+    assert np.array_equal(a[:, :, :, 0, 0].astype(np.complex64), wf[:, 3, :, :, 0].cpu().numpy())
+    (c.output_dir / "frame_1.npy").unlink()
+    d = MultisliceCalculator()
+    d.setup(traj, aperture=20.0, voltage_eV=100e3, probe_positions=pp, frame_cache=tmp_path)
+    wf2 = d.run().wavefunction_data
+    assert (d.frames_computed, d.frames_cached) == (1, 4)
+    assert torch.equal(wf, wf2)
+
+
+def test_linearity_in_the_probe_and_time_parseval():
+    """Properties at a fused-kernel grid (256 x 256, 40 slices): Propagate is linear in the probe, and the TACAW
+    cube obeys Parseval along time: sum_w I(w, k) = T * sum_t |psi_t(k) - <psi(k)>|^2."""
+    from pyslice_b200 import engine, hostmath, synthetic
+    from pyslice_b200.postprocessing.tacaw_data import TACAWData
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    traj = synthetic.random_trajectory(n_atoms=1500, box=(25.55, 25.55, 20.1), n_frames=6, seed=17, types=(14, 31))
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    t = engine.build_transmission(plan, dev(traj.positions[:2]))
+    g = torch.Generator(device="cuda").manual_seed(3)
+    p = torch.randn((2, 256, 256), generator=g, device="cuda", dtype=torch.float32) + 0j
+    p = p.to(torch.complex64)
+    both = torch.stack([p[0], p[1], (0.3 - 1.1j) * p[0] + (2.0 + 0.5j) * p[1]])
+    out = engine.propagate(plan, both, t)                     # (F, P, nx, ny) real-space exit waves
+    lin = (0.3 - 1.1j) * out[:, 0] + (2.0 + 0.5j) * out[:, 1]
+    assert rel_l2(out[:, 2].cpu().numpy(), lin.cpu().numpy()) < 2e-6
+
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=0.0, voltage_eV=100e3)
+    wf = calc.run()
+    tac = TACAWData(wf)
+    psi = wf.wavefunction_data[0, :, :, :, 0].to(torch.complex128)
+    want = psi.shape[0] * ((psi - psi.mean(dim=0, keepdim=True)).abs() ** 2).sum(dim=0)
+    got = tac.intensity[0].double().sum(dim=0)
+    assert float((got - want).abs().max() / want.abs().max()) < 1e-5
+
+
+@pytest.mark.parametrize("config", ["c3", "c4"])
+def test_full_size_properties_other_grids(config):
+    """Unitarity and determinism at the other benchmark grids: C3 512 x 512 x 67 (9 600 atoms, three types, 4 convergent
+    probes, fused kernels) and C4 1024 x 1024 x 123 (38 400 atoms, plane wave, generic line passes), one frame each."""
+    from pyslice_b200 import synthetic
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    from pyslice_b200.multislice.multislice import probe_grid
+    if config == "c3":
+        traj = synthetic.hbn_graphene_trajectory(n_frames=1, seed=2)
+        pp, ap, grid = [tuple(q) for q in probe_grid([10, 40], [12, 38], 2, 2)], 30.0, (512, 512, 67)
+    else:
+        traj = synthetic.silicon_trajectory(cells=(20, 20, 12), a=5.1175, n_frames=1, seed=3, displacement="phonon")
+        pp, ap, grid = None, 0.0, (1024, 1024, 123)
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=ap, voltage_eV=100e3, probe_positions=pp)
+    assert (calc.nx, calc.ny, calc.nz) == grid
+    wf1 = calc.run().wavefunction_data.clone()
+    wf2 = calc.run().wavefunction_data
+    assert torch.equal(wf1, wf2)
+    n = grid[0] * grid[1]
+    p0 = (calc._probes.abs().double() ** 2).sum(dim=(1, 2))                     # real-space probe power
+    power = (wf1.abs().double() ** 2).sum(dim=(2, 3, 4))[:, 0] / n             # Parseval: sum|FFT|^2 = n * sum|psi|^2
+    assert float((power / p0 - 1).abs().max()) < 1e-4
