@@ -2,6 +2,7 @@
 #include "../../include/pyslice_b200.h"
 
 #include "fast_path.h"
+#include "tacaw_fast.h"
 #include "line_pass.cuh"
 #include "potential_kernels.cuh"
 #include "psb_rt.h"
@@ -63,6 +64,7 @@ void psb_release_tables(void) {
 #ifndef PSB_EMU
     sf_fast_release();
     sf_cols_release();
+    tacaw_fast_release();
 #endif
 }
 long long psb_launch_count(void) { return launch_counter(); }
@@ -349,6 +351,11 @@ int psb_tacaw_intensity(const psb_c64* wf, long long stride_probe, long long str
     if (!wf || !intensity || n_probes < 0 || n_frames < 1 || npix < 0) return fail(PSB_ERR_INVALID, "psb_tacaw_intensity: bad argument");
     if (npix > 0x7fffffffLL) return fail(PSB_ERR_UNSUPPORTED, "psb_tacaw_intensity: npix too large");
     if (n_probes > 65535) return fail(PSB_ERR_UNSUPPORTED, "psb_tacaw_intensity: more than 65535 probes");
+#ifndef PSB_EMU
+    // frame counts 2^a 3^b 5^c: tiled mixed-radix transform (tacaw_fast.cu); anything else: Bluestein line pass
+    if (fast_path_enabled() && tacaw_fast_supported(n_frames))
+        return launch_tacaw_fast(f2(wf), stride_probe, stride_frame, n_probes, n_frames, npix, intensity, as_stream(stream));
+#endif
     PassParams p = base_params();
     p.src = f2(wf); p.src_img_stride = stride_probe;
     p.nlines = (int)npix; p.line_len = n_frames; p.line_stride = 1; p.elem_stride = stride_frame;

@@ -200,8 +200,9 @@ def test_hbn_multi_type_probes_vs_oracle():
             assert rel_l2(wf[p, f], ref[p, f]) < 1e-4
 
 
-@pytest.mark.parametrize("T", [20, 100, 500, 2000, 4000, 64])
+@pytest.mark.parametrize("T", [20, 100, 500, 2000, 4000, 64, 97, 14, 331, 45, 6, 2])
 def test_tacaw_time_fft_lengths(T):
+    # 2^a 3^b 5^c lengths run the tiled mixed-radix kernel (tacaw_fast.cu), 97 / 14 / 331 the Bluestein line pass
     from pyslice_b200 import engine
     rng = np.random.default_rng(T)
     P, nx, ny = 2, 8, 16
@@ -486,3 +487,28 @@ def test_full_size_properties_other_grids(config):
     p0 = (calc._probes.abs().double() ** 2).sum(dim=(1, 2))                     # real-space probe power
     power = (wf1.abs().double() ** 2).sum(dim=(2, 3, 4))[:, 0] / n             # Parseval: sum|FFT|^2 = n * sum|psi|^2
     assert float((power / p0 - 1).abs().max()) < 1e-4
+
+
+@pytest.mark.parametrize("T,nx,ny,P", [(100, 33, 7, 3), (500, 16, 24, 1), (20, 5, 5, 2), (2000, 4, 10, 1), (4000, 3, 3, 1)])
+def test_tacaw_tiled_kernel_vs_generic(T, nx, ny, P):
+    """tacaw_fast.cu against the generic line pass on the same input: pixel counts that do not fill the last tile, and
+    a layer view of a (L, P, T, nx, ny) store (frame stride != pixels per image is not needed, probe stride is)."""
+    from pyslice_b200 import engine
+    rng = np.random.default_rng(T + nx)
+    store = torch.from_numpy((rng.normal(size=(2, P, T, nx, ny)) + 1j * rng.normal(size=(2, P, T, nx, ny))
+                              + 3.0).astype(np.complex64)).cuda()
+    x = store[1]
+    out = {}
+    for level in (1, 0):
+        engine.set_fast_path(level)
+        try:
+            out[level] = engine.tacaw_intensity(x).cpu().numpy()
+        finally:
+            engine.set_fast_path(True)
+    dc = T // 2
+    keep = [i for i in range(T) if i != dc]
+    assert rel_l2(out[1][:, keep], out[0][:, keep]) < 2e-5
+    ref, _ = orc.tacaw_intensity(x.cpu().numpy().astype(np.complex128), np.arange(T) * 0.01)
+    assert rel_l2(out[1][:, keep], ref[:, keep]) < 1e-4
+    assert np.abs(out[1][:, dc]).max() <= 1e-6 * np.abs(ref).max() * T      # DC bin: rounding noise of the mean only
+    assert np.array_equal(out[1], engine.tacaw_intensity(x).cpu().numpy())  # deterministic
