@@ -305,6 +305,14 @@ struct ColPassParams {
     long long n_tiles;           // n_img * NY / W
 };
 
+// exchange buffers of the column pass: 2 alternate (one CTA barrier per exchange, 2 CTAs per SM by shared memory);
+// 1 needs a second barrier per exchange but lets 3 CTAs share an SM
+#ifndef PSB_COL_XBUFS
+#define PSB_COL_XBUFS 2
+#endif
+constexpr int kColXBufs = PSB_COL_XBUFS;
+constexpr int kColCtasPerSm = kColXBufs == 1 ? 3 : 2;
+
 template <int N>
 struct ColCfg {
     static constexpr int T = N / 16;
@@ -312,7 +320,7 @@ struct ColCfg {
     static constexpr int kPadRows = (W == 8) ? N / 16 : 0;            // keeps 8-column rows conflict-free
     static constexpr int kLand = N * W;                               // float2 (32 KB)
     static constexpr int kX = (N + kPadRows) * W;
-    static constexpr size_t kSmem = (size_t)(kLand + 2 * kX + N) * sizeof(float2) + 2 * sizeof(uint64_t);      // + NY*8 for Py, added at launch
+    static constexpr size_t kSmem = (size_t)(kLand + kColXBufs * kX + N) * sizeof(float2) + 2 * sizeof(uint64_t);      // + NY*8 for Py, added at launch
     static constexpr int kBoxRows = 256;                              // TMA box limit per dimension
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
 };
@@ -329,7 +337,7 @@ struct ColXchg {
     cpx* land;
     int next_c0, next_r0;        // tensor coordinates of the next tile; next_c0 < 0: nothing to prefetch
     int hook_i;                  // index of the tile's first exchange
-    __device__ __forceinline__ cpx* buf(int i) const { return (i & 1) ? b1 : b0; }
+    __device__ __forceinline__ cpx* buf(int i) const { return (kColXBufs == 2 && (i & 1)) ? b1 : b0; }
     __device__ __forceinline__ int at(int q) const {
         return (ColCfg<N>::W == 8 ? q + (q >> 4) : q) * ColCfg<N>::W + c;
     }
@@ -342,18 +350,20 @@ struct ColXchg {
                 tensor2d_g2s(land + h * ColCfg<N>::kBoxRows * ColCfg<N>::W, map, next_c0, next_r0 + h * ColCfg<N>::kBoxRows, mb);
         }
     }
-    __device__ __forceinline__ void after_load(int) const {}
+    __device__ __forceinline__ void after_load(int) const {
+        if (kColXBufs == 1) __syncthreads();
+    }
 };
 
 enum ColMode { C_PROPAGATE = 0, C_INVERSE = 1 };
 
 template <int N, int NY, int MODE>
-__global__ void __launch_bounds__(256, 2) fast_cols_kernel(const __grid_constant__ CUtensorMap tmap, const ColPassParams p) {
+__global__ void __launch_bounds__(256, kColCtasPerSm) fast_cols_kernel(const __grid_constant__ CUtensorMap tmap, const ColPassParams p) {
     using C = ColCfg<N>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* land = reinterpret_cast<cpx*>(smem_raw);
     cpx* xb0 = land + C::kLand;
-    cpx* xb1 = xb0 + C::kX;
+    cpx* xb1 = xb0 + (kColXBufs - 1) * C::kX;
     cpx* spx = xb1 + C::kX;
     cpx* spy = spx + N;
     uint64_t* mb = reinterpret_cast<uint64_t*>(spy + NY);
@@ -502,7 +512,7 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const fl
     ColPassParams p;
     p.psi = psi; p.px = px; p.py = py; p.tw = tw;
     p.n_tiles = (long long)n_img * (NY / C::W);
-    const long long slots = 2LL * rt::sm_count();
+    const long long slots = (long long)kColCtasPerSm * rt::sm_count();
     const int grid = (int)(p.n_tiles < slots ? p.n_tiles : slots);
     cudaError_t e = pdl_launch(fast_cols_kernel<N, NY, MODE>, dim3(grid), dim3(256), C::kSmem + NY * sizeof(float2), s, map, p);
     ++launch_counter();

@@ -8,4 +8,8 @@ if os.environ.get("PSB_VARIANT_LIB"):
 if os.environ.get("PSB_SCRATCH_MB"):
     engine.SCRATCH_BYTES = int(os.environ["PSB_SCRATCH_MB"]) << 20
 sys.argv = sys.argv[1:]
-runpy.run_path(sys.argv[0], run_name="__main__")
+if sys.argv[0] == "-m":                      # python tools/run_variant.py -m pytest tests ...
+    sys.argv = sys.argv[1:]
+    runpy.run_module(sys.argv[0], run_name="__main__", alter_sys=True)
+else:
+    runpy.run_path(sys.argv[0], run_name="__main__")
