@@ -65,6 +65,17 @@ def split_frames(n_frames: int, world: int) -> List[int]:
     return [n_frames // world + (1 if r < n_frames % world else 0) for r in range(world)]
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device) -> "torch.cuda.Stream":
+    """one side stream per device for host -> device copies that overlap the kernels of the main stream"""
+    key = (device.type, device.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
 class _FrameWriter:
     """Background writer of the per-frame cache files: (P, nx, ny) complex64 host tensors in, `.npy` files of shape
     (P, nx, ny, 1, 1) complex128 out (the reference's wire format)."""
@@ -252,26 +263,46 @@ class MultisliceCalculator:
                 j += 1
             runs.append((i, j))
             i = j
-        for r0, r1 in runs:
-            for b0 in range(r0, r1, fb):
-                nb = min(fb, r1 - b0)
-                block = positions[f_lo + b0:f_lo + b0 + nb]
-                if isinstance(block, torch.Tensor):      # already resident (device arm of bench.py)
-                    pos_d = block.to(device=self.device, dtype=torch.float64).contiguous()
-                else:
-                    pos = np.ascontiguousarray(block, dtype=np.float64)
-                    pos_d = torch.from_numpy(pos).to(self.device, non_blocking=True)
-                with timer.phase("potential"):
-                    t = engine.build_transmission(plan, pos_d, out=tbuf[:nb])
-                with timer.phase("propagate"):
-                    for p0 in range(0, P, pb):
-                        np_ = min(pb, P - p0)
-                        engine.propagate(plan, self._probes[p0:p0 + np_], t, wf_out=store, frame0=b0, probe0=p0,
-                                         layer_every=self.layer_every, work=work)
-                if writer is not None:
-                    host = store[0, :, b0:b0 + nb].to("cpu")                 # (P, nb, nx, ny); synchronises this batch
-                    for k in range(nb):
-                        writer.put(self._cache_file(f_lo + b0 + k), host[:, k])
+        batches = [(b0, min(fb, r1 - b0)) for r0, r1 in runs for b0 in range(r0, r1, fb)]
+        # Host positions go up on a copy stream, every batch queued before the first kernel: only the first batch's
+        # copy (a few MB) is exposed, the rest overlap the compute of earlier batches (pinned host memory; pageable
+        # memory degrades to a staged copy but stays correct)
+        uploads = {}
+        if batches and not isinstance(positions, torch.Tensor) and self.device.type == "cuda":
+            main = torch.cuda.current_stream(self.device)
+            side = _copy_stream(self.device)
+            dev_pos = torch.empty((T_loc,) + tuple(positions.shape[1:]), dtype=torch.float64, device=self.device)
+            ready = torch.cuda.Event()
+            ready.record(main)                              # the buffer's previous life on the main stream is over
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                for b0, nb in batches:
+                    pos = np.ascontiguousarray(positions[f_lo + b0:f_lo + b0 + nb], dtype=np.float64)
+                    dev_pos[b0:b0 + nb].copy_(torch.from_numpy(pos), non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+                    uploads[b0] = (dev_pos[b0:b0 + nb], ev)
+        for b0, nb in batches:
+            block = positions[f_lo + b0:f_lo + b0 + nb]
+            if b0 in uploads:
+                pos_d, ev = uploads.pop(b0)
+                torch.cuda.current_stream(self.device).wait_event(ev)
+            elif isinstance(block, torch.Tensor):      # already resident (device arm of bench.py)
+                pos_d = block.to(device=self.device, dtype=torch.float64).contiguous()
+            else:
+                pos = np.ascontiguousarray(block, dtype=np.float64)
+                pos_d = torch.from_numpy(pos).to(self.device, non_blocking=True)
+            with timer.phase("potential"):
+                t = engine.build_transmission(plan, pos_d, out=tbuf[:nb])
+            with timer.phase("propagate"):
+                for p0 in range(0, P, pb):
+                    np_ = min(pb, P - p0)
+                    engine.propagate(plan, self._probes[p0:p0 + np_], t, wf_out=store, frame0=b0, probe0=p0,
+                                     layer_every=self.layer_every, work=work)
+            if writer is not None:
+                host = store[0, :, b0:b0 + nb].to("cpu")                 # (P, nb, nx, ny); synchronises this batch
+                for k in range(nb):
+                    writer.put(self._cache_file(f_lo + b0 + k), host[:, k])
         if writer is not None:
             writer.close()
             if self.cleanup_temp_files:                   # reference calculators.py:235-245
