@@ -72,6 +72,15 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
                            float scale, float sigma, psb_c64* t_out, float* v_out, psb_c64* scratch,
                            long long scratch_elems, void* stream);
 
+/* The same build with the stack kept as float32 phases sigma*V[f, z, x, y] (4 B per pixel and slice instead of 8):
+ * multislice.py:281-282 evaluates exp(i*sigma*V) per slice anyway, psb_propagate_phase does so inside its fused row
+ * pass.  Worth it when few probes share a frame's stack (plane-wave runs: written once, read once).  Grids with fused
+ * kernels only (psb_phase_format_supported), PSB_ERR_UNSUPPORTED otherwise. */
+int psb_build_phase(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
+                    int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
+                    float scale, float sigma, float* phase_out, psb_c64* scratch, long long scratch_elems, void* stream);
+int psb_phase_format_supported(int nx, int ny);
+
 /* t = exp(i*sigma*V) for a user-supplied real potential (Propagate() on a Potential object) */
 int psb_transmission_from_potential(const float* v, psb_c64* t, long long n, float sigma, void* stream);
 
@@ -95,6 +104,12 @@ int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_p
                   const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out,
                   long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
                   void* stream);
+
+/* psb_propagate on a phase stack from psb_build_phase; t0 (n_frames, nx, ny) is scratch for exp(i*phase) of slice 0 */
+int psb_propagate_phase(const psb_c64* probes, const float* phase, psb_c64* t0, int n_frames, int n_probes, int nz, int nx,
+                        int ny, const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out,
+                        long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
+                        void* stream);
 
 /* ---- TACAW: tacaw_data.py:89-104.  intensity[p, w, pix] = |fftshift_t FFT_t(psi - mean_t psi)|^2
  * wf element (p, f, pix) at wf[p*stride_probe + f*stride_frame + pix]; intensity (P, T, npix) float32. */

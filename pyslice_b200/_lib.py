@@ -37,6 +37,9 @@ _SIGNATURES = {
     "psb_transmission_from_potential": (C.c_int, [_P, _P, _LL, _F, _P]),
     "psb_fft2": (C.c_int, [_P, _P, _I, _I, _I, _I, _F, _P]),
     "psb_shift_probes": (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P]),
+    "psb_build_phase": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _P, _P, _LL, _P]),
+    "psb_phase_format_supported": (C.c_int, [_I, _I]),
+    "psb_propagate_phase": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _LL, _LL, _LL, _I, _P]),
     "psb_propagate": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _LL, _LL, _LL, _I, _P]),
     "psb_tacaw_intensity": (C.c_int, [_P, _LL, _LL, _I, _I, _LL, _P, _P]),
     "psb_sum_pixels": (C.c_int, [_P, _P, _I, _LL, _LL, _P, _P]),

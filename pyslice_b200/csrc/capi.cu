@@ -113,12 +113,19 @@ int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames
     return rc;
 }
 
-int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
-                           int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
-                           float scale, float sigma, psb_c64* t_out, float* v_out, psb_c64* scratch,
-                           long long scratch_elems, void* stream) {
-    if (!offsets || !ux || !uy || !formfactors || !t_out || !scratch)
+// phase_out != nullptr: the stack is written as float32 phases sigma*V instead of t = exp(i*sigma*V) (fused grids only)
+static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
+                      int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
+                      float scale, float sigma, psb_c64* t_out, float* v_out, float* phase_out, psb_c64* scratch,
+                      long long scratch_elems, void* stream) {
+    if (!offsets || !ux || !uy || !formfactors || (!t_out && !phase_out) || !scratch)
         return fail(PSB_ERR_INVALID, "psb_build_transmission: null pointer");
+#ifndef PSB_EMU
+    if (phase_out && !fast_slice_supported(nx, ny))
+#else
+    if (phase_out)
+#endif
+        return fail(PSB_ERR_UNSUPPORTED, "psb_build_phase: the phase format needs a grid with fused kernels (256 / 512 points)");
     if (n_frames < 0 || nz < 1 || nx < 1 || ny < 1 || ntypes < 1) return fail(PSB_ERR_INVALID, "psb_build_transmission: bad sizes");
     if (n_frames == 0) return PSB_OK;
     cudaStream_t s = as_stream(stream);
@@ -147,6 +154,17 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
         if (rc0 != PSB_OK) return rc0;
     }
 #endif
+#ifndef PSB_EMU
+    // inverse row transform of a chunk + epilogue: t = exp(i*sigma*V) (and optionally V), or the bare phases
+    auto rows_out = [&](int nf, int nm, int f0, int mb) {
+        const float norm = scale / ((float)nx * (float)ny);
+        if (phase_out)
+            return launch_fast_rows_phase_out(f2(scratch), nf * nm, nx, ny, norm, sigma, phase_out + (long long)f0 * nz * img,
+                                              nm, nz, mb, s);
+        return launch_fast_rows_transmit(f2(scratch), nf * nm, nx, ny, norm, sigma, f2(t_out) + (long long)f0 * nz * img,
+                                         v_out ? v_out + (long long)f0 * nz * img : nullptr, nm, nz, mb, s);
+    };
+#endif
     for (int f0 = 0; f0 < n_frames; f0 += fc) {
         const int nf = n_frames - f0 < fc ? n_frames - f0 : fc;
         for (int mb = 0; mb < npairs; mb += mc) {
@@ -171,9 +189,7 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
                 // inverse row transform with the transmission epilogue
                 rc = launch_sf_cols(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, sf_fast_ff4(), f2(scratch), s);
                 if (rc != PSB_OK) return rc;
-                rc = launch_fast_rows_transmit(f2(scratch), nf * nm, nx, ny, scale / ((float)nx * (float)ny), sigma,
-                                               f2(t_out) + (long long)f0 * nz * img,
-                                               v_out ? v_out + (long long)f0 * nz * img : nullptr, nm, nz, mb, s);
+                rc = rows_out(nf, nm, f0, mb);
                 if (rc != PSB_OK) return rc;
                 continue;
             }
@@ -188,9 +204,7 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
             if (fast_slice_supported(nx, ny)) {      // persistent TMA kernels (fast_path.cu), same arithmetic
                 rc = launch_fast_cols_inverse(f2(scratch), nf * nm, nx, ny, s);
                 if (rc != PSB_OK) return rc;
-                rc = launch_fast_rows_transmit(f2(scratch), nf * nm, nx, ny, scale / ((float)nx * (float)ny), sigma,
-                                               f2(t_out) + (long long)f0 * nz * img,
-                                               v_out ? v_out + (long long)f0 * nz * img : nullptr, nm, nz, mb, s);
+                rc = rows_out(nf, nm, f0, mb);
                 if (rc != PSB_OK) return rc;
                 continue;
             }
@@ -211,6 +225,32 @@ int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uin
         }
     }
     return PSB_OK;
+}
+
+int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
+                           int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
+                           float scale, float sigma, psb_c64* t_out, float* v_out, psb_c64* scratch,
+                           long long scratch_elems, void* stream) {
+    if (!t_out) return fail(PSB_ERR_INVALID, "psb_build_transmission: null pointer");
+    return build_impl(offsets, ux, uy, n_frames, n_atoms, nz, ntypes, nx, ny, formfactors, scale, sigma, t_out, v_out, nullptr,
+                      scratch, scratch_elems, stream);
+}
+
+int psb_build_phase(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
+                    int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
+                    float scale, float sigma, float* phase_out, psb_c64* scratch, long long scratch_elems, void* stream) {
+    if (!phase_out) return fail(PSB_ERR_INVALID, "psb_build_phase: null pointer");
+    return build_impl(offsets, ux, uy, n_frames, n_atoms, nz, ntypes, nx, ny, formfactors, scale, sigma, nullptr, nullptr,
+                      phase_out, scratch, scratch_elems, stream);
+}
+
+int psb_phase_format_supported(int nx, int ny) {
+#ifndef PSB_EMU
+    return fast_slice_supported(nx, ny) ? 1 : 0;
+#else
+    (void)nx; (void)ny;
+    return 0;
+#endif
 }
 
 int psb_transmission_from_potential(const float* v, psb_c64* t, long long n, float sigma, void* stream) {
@@ -263,11 +303,14 @@ int psb_shift_probes(const psb_c64* base_k, const psb_c64* ramp_x, const psb_c64
     return launch_line_pass(PASS_INV_ROWS, p, n_probes, s);
 }
 
-int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_probes, int nz, int nx, int ny,
-                  const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out,
-                  long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
-                  void* stream) {
-    if (!probes || !t || !prop_x || !prop_y || !psi_work) return fail(PSB_ERR_INVALID, "psb_propagate: null pointer");
+// phase != nullptr: the stack holds float32 phases; t0 (n_frames, nx, ny) receives exp(i*phase) of slice 0 for the
+// generic first pass, every later slice is evaluated inside the fused row pass
+static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* phase, psb_c64* t0, int n_frames, int n_probes,
+                          int nz, int nx, int ny, const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode,
+                          psb_c64* wf_out, long long stride_probe, long long stride_frame, long long stride_layer,
+                          int layer_every, void* stream) {
+    if (!probes || (!t && !phase) || !prop_x || !prop_y || !psi_work) return fail(PSB_ERR_INVALID, "psb_propagate: null pointer");
+    if (phase && !t0) return fail(PSB_ERR_INVALID, "psb_propagate_phase: t0 scratch required");
     if (mode != 0 && mode != 1) return fail(PSB_ERR_INVALID, "psb_propagate: mode must be 0 or 1");
     if (mode == 1 && !wf_out) return fail(PSB_ERR_INVALID, "psb_propagate: wf_out required in mode 1");
     if (n_frames < 0 || n_probes < 1 || nz < 1 || nx < 1 || ny < 1 || layer_every < 0)
@@ -303,13 +346,24 @@ int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_p
 #else
     const bool fast = false;
 #endif
+    if (phase) {
+        if (!fast) return fail(PSB_ERR_UNSUPPORTED, "psb_propagate_phase: the phase format needs a grid with fused kernels");
+        for (int f = 0; f < n_frames; ++f) {        // slice 0 of every frame as t for the generic first pass
+            int rc0 = psb_transmission_from_potential(phase + (long long)f * nz * img, t0 + (long long)f * img, img, 1.0f, stream);
+            if (rc0 != PSB_OK) return rc0;
+        }
+        row.mul_img_stride = img;
+    }
     int layer = 0;
     for (int z = 0; z < nz; ++z) {
-        row.mul = f2(t) + (long long)z * img;
+        row.mul = phase ? f2(t0) : f2(t) + (long long)z * img;
         int rc;
         if (z > 0 && fast) {
 #ifndef PSB_EMU
-            rc = launch_fast_rows(f2(psi_work), n_img, nx, ny, f2(t) + (long long)z * img, (long long)nz * img, n_probes, s);
+            if (phase)
+                rc = launch_fast_rows_phase(f2(psi_work), n_img, nx, ny, phase + (long long)z * img, (long long)nz * img, n_probes, s);
+            else
+                rc = launch_fast_rows(f2(psi_work), n_img, nx, ny, f2(t) + (long long)z * img, (long long)nz * img, n_probes, s);
 #endif
         } else if (z == 0) {
             row.src = f2(probes); row.src_img_stride = img; row.src_img_mod = n_probes;
@@ -344,6 +398,24 @@ int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_p
         return launch_line_pass(PASS_INV_ROWS, inv, n_img, s);
     }
     return PSB_OK;
+}
+
+int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_probes, int nz, int nx, int ny,
+                  const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out,
+                  long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
+                  void* stream) {
+    if (!t) return fail(PSB_ERR_INVALID, "psb_propagate: null pointer");
+    return propagate_impl(probes, t, nullptr, nullptr, n_frames, n_probes, nz, nx, ny, prop_x, prop_y, psi_work, mode, wf_out,
+                          stride_probe, stride_frame, stride_layer, layer_every, stream);
+}
+
+int psb_propagate_phase(const psb_c64* probes, const float* phase, psb_c64* t0, int n_frames, int n_probes, int nz, int nx,
+                        int ny, const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out,
+                        long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
+                        void* stream) {
+    if (!phase) return fail(PSB_ERR_INVALID, "psb_propagate_phase: null pointer");
+    return propagate_impl(probes, nullptr, phase, t0, n_frames, n_probes, nz, nx, ny, prop_x, prop_y, psi_work, mode, wf_out,
+                          stride_probe, stride_frame, stride_layer, layer_every, stream);
 }
 
 int psb_tacaw_intensity(const psb_c64* wf, long long stride_probe, long long stride_frame, int n_probes,

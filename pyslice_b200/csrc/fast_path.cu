@@ -116,6 +116,20 @@ __device__ __forceinline__ void pair_cis(cpx x, cpx& ea, cpx& eb) {
     eb = fast::c_make(cb, sb);
 }
 
+#ifdef PSB_NO_STCS
+#define __stcs(ptr, val) (*(ptr) = (val))
+#endif
+
+// exp(i*x) for one phase (R_STEP_PHASE): the scalar form of pair_cis
+__device__ __forceinline__ cpx cis1(float x) {
+    float k = fmaf(x, 0.15915494309189535f, 12582912.f) - 12582912.f;
+    float r = fmaf(k, -6.2831854820251465f, x);
+    r = fmaf(k, 1.7484555e-7f, r);
+    float sn, cs;
+    __sincosf(r, &sn, &cs);
+    return fast::c_make(cs, sn);
+}
+
 // ---- row pass ------------------------------------------------------------------------------------------
 struct RowPassParams {
     float2* psi;                 // (n_img, nx, N) contiguous, transformed in place
@@ -133,7 +147,11 @@ struct RowPassParams {
     int pair_count, pair_nz, pair_begin;
 };
 
-enum RowMode { R_STEP = 0, R_TRANSMIT = 1 };
+// R_PHASE / R_STEP_PHASE: the transmission stack as float32 phases sigma*V (4 B per pixel and slice instead of 8):
+// R_PHASE writes them (no sincos), R_STEP_PHASE reads them and evaluates exp(i*phase) on the SFU as it multiplies.
+// Worth it when few probes share a frame's stack (plane-wave runs): the stack is written once and read once per probe.
+enum RowMode { R_STEP = 0, R_TRANSMIT = 1, R_PHASE = 2, R_STEP_PHASE = 3 };
+constexpr bool row_mode_steps(int mode) { return mode == R_STEP || mode == R_STEP_PHASE; }
 
 // transmission landing buffers per warp (R_STEP): with 2 the copy of unit n+2's rows is issued while unit n is
 // transformed, a full unit of lead more against the HBM round trip, at the price of 12 instead of 16 warps per SM
@@ -155,6 +173,7 @@ struct RowCfg {
     static constexpr int kBars = 1 + kTBufs;
     static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + kWarps * kBars * sizeof(uint64_t);
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
+    static constexpr uint32_t kTBytes = kLand * (MODE == 3 ? sizeof(float) : sizeof(float2));     // transmission rows of a unit
 };
 
 template <int N>
@@ -203,10 +222,12 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
     const int upi_shift = 31 - __clz(p.nx / C::LPW);          // log2(units per image)
     const int upi_mask = (1 << upi_shift) - 1;
 
-    auto t_rows = [&](int unit) {
+    auto t_rows = [&](int unit) -> const void* {
         const unsigned img = (unsigned)unit >> upi_shift;
         const int row0 = (unit & upi_mask) * C::LPW;
-        return p.t + (long long)(img / (unsigned)p.probes) * p.t_frame_stride + row0 * N;
+        const long long o = (long long)(img / (unsigned)p.probes) * p.t_frame_stride + row0 * N;
+        if (MODE == R_STEP_PHASE) return reinterpret_cast<const float*>(p.t) + o;
+        return p.t + o;
     };
     auto issue = [&](int unit, bool want_psi, bool want_t, int tb = 0) {
         if (want_psi) {
@@ -214,15 +235,15 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
 #ifdef PSB_NO_EVICT
             if (false)
 #else
-            if (MODE == R_TRANSMIT)      // last use of the chunk's rows: do not let them displace the next chunk's
+            if (MODE == R_TRANSMIT || MODE == R_PHASE)      // last use of the chunk's rows: do not let them displace the next chunk's
 #endif
                 bulk_g2s_hint(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi, stream_once);
             else
                 bulk_g2s(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi);
         }
-        if (MODE == R_STEP && want_t) {
-            mbar_expect_tx(mb_t + tb, C::kBytes);
-            bulk_g2s_hint(land_t + tb * C::kLand, t_rows(unit), C::kBytes, mb_t + tb, stream_once);
+        if (row_mode_steps(MODE) && want_t) {
+            mbar_expect_tx(mb_t + tb, C::kTBytes);
+            bulk_g2s_hint(land_t + tb * C::kLand, t_rows(unit), C::kTBytes, mb_t + tb, stream_once);
         }
     };
     if (u < n_units && lane == 0) {
@@ -245,12 +266,17 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
         // (Issuing right after a __syncwarp let the next unit's TMA overwrite words whose LDS was still in flight.)
         const cpx* lp = land_psi + c * N + j;
         const cpx* lt = land_t + tb * C::kLand + c * N + j;
-        if constexpr (MODE == R_STEP) {
+        if constexpr (row_mode_steps(MODE)) {
             cpx v[16];
+            const float* ltf = reinterpret_cast<const float*>(land_t) + c * N + j;      // R_STEP_PHASE: float rows
             // psi[x, ky] -> IFFT_y -> * t[x, y]
             fast::line_fft<N, +1>(
                 [&](int e) { return lp[e * C::T]; },
-                [&](int e, cpx a) { v[e] = fast::cmulp(a, lt[e * C::T]); }, tw, j, xc, 0,
+                [&](int e, cpx a) {
+                    if constexpr (MODE == R_STEP_PHASE) v[e] = fast::cmulp(a, cis1(ltf[e * C::T]));
+                    else v[e] = fast::cmulp(a, lt[e * C::T]);
+                },
+                tw, j, xc, 0,
                 [&]() {
                     if (lane == 0 && next) issue(un, true, false);
                 },
@@ -275,12 +301,15 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
                 [&](int e) { return lp[e * C::T]; },
                 [&](int e, cpx a) {
                     const cpx V2 = fast::mul2(a, scale2);         // (V_2m, V_2m+1)
+                    if constexpr (MODE == R_PHASE) {              // phases sigma*V of the two slices, no sincos
+                        const cpx ph = fast::mul2(V2, sigma2);
+                        __stcs(p.v_out + o + e * C::T, fast::c_re(ph));
+                        if (has_b) __stcs(p.v_out + o + img_elems + e * C::T, fast::c_im(ph));
+                        return;
+                    }
                     cpx ta, tb;
                     pair_cis(fast::mul2(V2, sigma2), ta, tb);
                     // streaming stores: t (134 MB per 64 MB chunk of spectra) must not evict the L2-resident chunk
-#ifdef PSB_NO_STCS
-#define __stcs(ptr, val) (*(ptr) = (val))
-#endif
                     __stcs(ta_out + e * C::T, ta);
                     if (p.v_out) __stcs(p.v_out + o + e * C::T, fast::c_re(V2));
                     if (has_b) {
@@ -544,6 +573,38 @@ int launch_fast_rows(float2* psi, int n_img, int nx, int ny, const float2* t_sli
     }
     p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
     return rows_go<512, R_STEP>(p, s);
+}
+
+int launch_fast_rows_phase(float2* psi, int n_img, int nx, int ny, const float* phase_slice, long long t_frame_stride,
+                           int probes, cudaStream_t s) {
+    RowPassParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = psi; p.t = reinterpret_cast<const float2*>(phase_slice); p.t_frame_stride = t_frame_stride; p.probes = probes; p.nx = nx;
+    int rc = twiddles_for(ny, &p.tw, s);
+    if (rc != PSB_OK) return rc;
+    if (ny == 256) {
+        p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
+        return rows_go<256, R_STEP_PHASE>(p, s);
+    }
+    p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
+    return rows_go<512, R_STEP_PHASE>(p, s);
+}
+
+int launch_fast_rows_phase_out(float2* pairs, int n_img, int nx, int ny, float scale, float sigma, float* phase_out,
+                               int pair_count, int pair_nz, int pair_begin, cudaStream_t s) {
+    RowPassParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.psi = pairs; p.nx = nx; p.probes = 1;
+    p.v_out = phase_out; p.scale = scale; p.sigma = sigma;
+    p.pair_count = pair_count; p.pair_nz = pair_nz; p.pair_begin = pair_begin;
+    int rc = twiddles_for(ny, &p.tw, s);
+    if (rc != PSB_OK) return rc;
+    if (ny == 256) {
+        p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
+        return rows_go<256, R_PHASE>(p, s);
+    }
+    p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
+    return rows_go<512, R_PHASE>(p, s);
 }
 
 int launch_fast_rows_transmit(float2* pairs, int n_img, int nx, int ny, float scale, float sigma, float2* t_out,

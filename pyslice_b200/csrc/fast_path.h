@@ -26,6 +26,13 @@ int launch_fast_cols_inverse(float2* imgs, int n_img, int nx, int ny, cudaStream
 int launch_fast_rows_transmit(float2* pairs, int n_img, int nx, int ny, float scale, float sigma, float2* t_out,
                               float* v_out, int pair_count, int pair_nz, int pair_begin, cudaStream_t s);
 
+// the same two passes with the transmission stack kept as float32 phases sigma*V (t = exp(i*phase) is evaluated by the
+// slice step as it multiplies): phase_out / phase_slice are indexed like t_out / t_slice
+int launch_fast_rows_phase(float2* psi, int n_img, int nx, int ny, const float* phase_slice, long long t_frame_stride,
+                           int probes, cudaStream_t s);
+int launch_fast_rows_phase_out(float2* pairs, int n_img, int nx, int ny, float scale, float sigma, float* phase_out,
+                               int pair_count, int pair_nz, int pair_begin, cudaStream_t s);
+
 // structure-factor sum of slice pairs [pair_begin, pair_begin + pair_count) of nf frames into out (nf, pair_count, nx, ny)
 // (sf_fast.cu: precomputed phase tables + TMA-fed packed-FMA tiles); any grid size
 // sf_fast_prepare gathers the form-factor table once per psb_build_transmission call; launch_sf_fast runs per chunk

@@ -219,20 +219,34 @@ def chunk_images(plan: SlicePlan, n_frames: int) -> int:
     return want
 
 
+def phase_format_supported(plan: SlicePlan) -> bool:
+    """True when the transmission stack of this grid may be kept as float32 phases (fused kernels: 256 / 512 points)."""
+    return bool(_lib.lib().psb_phase_format_supported(plan.nx, plan.ny))
+
+
 def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential: bool = False,
-                       out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None):
-    """positions (F, A, 3) float64 on device -> t (F, nz, nx, ny) complex64 [, V float32]."""
+                       out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None, phase: bool = False):
+    """positions (F, A, 3) float64 on device -> t (F, nz, nx, ny) complex64 [, V float32].
+    phase=True: the stack as float32 phases sigma*V instead (half the bytes; `propagate` accepts either)."""
     F, A, _ = positions.shape
     dev = plan.device
     offsets, _, ux, uy = bin_atoms(plan, positions)
-    t = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device=dev)
-    V = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev) if want_potential else None
     scale = 1.0 / (plan.dx ** 2 * plan.dy ** 2)
     img = plan.nx * plan.ny
     n_scratch = img * chunk_images(plan, F)
     if scratch is None or scratch.numel() < n_scratch:
         scratch = torch.empty((n_scratch,), dtype=torch.complex64, device=dev)
     L = _lib.lib()
+    if phase:
+        assert not want_potential
+        ph = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev)
+        assert ph.dtype == torch.float32
+        _lib.check(L.psb_build_phase(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
+                                     plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
+                                     ph.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(dev)), "psb_build_phase")
+        return ph
+    t = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device=dev)
+    V = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev) if want_potential else None
     _lib.check(L.psb_build_transmission(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
                                         plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
                                         t.data_ptr(), V.data_ptr() if V is not None else None, scratch.data_ptr(),
@@ -278,18 +292,26 @@ def propagate(plan: SlicePlan, probes: torch.Tensor, t: torch.Tensor, wf_out: Op
     if work is None:
         work = torch.empty((F * P, nx, ny), dtype=torch.complex64, device=plan.device)
     L = _lib.lib()
+    st = _stream(plan.device)
+    if t.dtype == torch.float32:                 # phase stack (build_transmission(phase=True))
+        t0 = torch.empty((F, nx, ny), dtype=torch.complex64, device=plan.device)
+
+        def call(mode, base, sp, sf, sl, le):
+            return L.psb_propagate_phase(probes.data_ptr(), t.data_ptr(), t0.data_ptr(), F, P, nz, nx, ny,
+                                         plan.prop_x.data_ptr(), plan.prop_y.data_ptr(), work.data_ptr(), mode, base, sp, sf, sl,
+                                         le, st)
+    else:
+        def call(mode, base, sp, sf, sl, le):
+            return L.psb_propagate(probes.data_ptr(), t.data_ptr(), F, P, nz, nx, ny, plan.prop_x.data_ptr(),
+                                   plan.prop_y.data_ptr(), work.data_ptr(), mode, base, sp, sf, sl, le, st)
     if wf_out is None:
-        _lib.check(L.psb_propagate(probes.data_ptr(), t.data_ptr(), F, P, nz, nx, ny, plan.prop_x.data_ptr(),
-                                   plan.prop_y.data_ptr(), work.data_ptr(), 0, None, 0, 0, 0, 0, _stream(plan.device)),
-                   "psb_propagate")
+        _lib.check(call(0, None, 0, 0, 0, 0), "psb_propagate")
         return work.view(F, P, nx, ny)
     Lr, Pt, Tt = wf_out.shape[:3]
     assert wf_out.is_contiguous() and Lr == layer_count(nz, layer_every)
     img = nx * ny
     base = wf_out.data_ptr() + 8 * (probe0 * Tt * img + frame0 * img)
-    _lib.check(L.psb_propagate(probes.data_ptr(), t.data_ptr(), F, P, nz, nx, ny, plan.prop_x.data_ptr(),
-                               plan.prop_y.data_ptr(), work.data_ptr(), 1, base, Tt * img, img, Pt * Tt * img,
-                               layer_every, _stream(plan.device)), "psb_propagate")
+    _lib.check(call(1, base, Tt * img, img, Pt * Tt * img, layer_every), "psb_propagate")
     return wf_out
 
 

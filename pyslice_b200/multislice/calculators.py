@@ -236,7 +236,10 @@ class MultisliceCalculator:
         store = torch.empty((self.n_layers, P, T_loc, nx, ny), dtype=torch.complex64, device=self.device)
         fb, pb = engine.batch_sizes(plan, P, max(T_loc, 1))
         work = torch.empty((fb * min(pb, P), nx, ny), dtype=torch.complex64, device=self.device)
-        tbuf = torch.empty((fb, plan.nz, nx, ny), dtype=torch.complex64, device=self.device)
+        # one probe per frame: the stack is written once and read once, so it is kept as float32 phases (half the HBM
+        # traffic, exp(i*phase) evaluated inside the fused slice step); shared by several probes it stays complex64
+        use_phase = P == 1 and engine.phase_format_supported(plan)
+        tbuf = torch.empty((fb, plan.nz, nx, ny), dtype=torch.float32 if use_phase else torch.complex64, device=self.device)
         positions = self.trajectory.positions
         # frame cache (opt-in): cached frames are loaded, the others are computed in contiguous runs and handed to
         # a writer thread (D2H on a side stream would buy nothing here: the files are written by the host anyway)
@@ -293,7 +296,7 @@ class MultisliceCalculator:
                 pos = np.ascontiguousarray(block, dtype=np.float64)
                 pos_d = torch.from_numpy(pos).to(self.device, non_blocking=True)
             with timer.phase("potential"):
-                t = engine.build_transmission(plan, pos_d, out=tbuf[:nb])
+                t = engine.build_transmission(plan, pos_d, out=tbuf[:nb], phase=use_phase)
             with timer.phase("propagate"):
                 for p0 in range(0, P, pb):
                     np_ = min(pb, P - p0)

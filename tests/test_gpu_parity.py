@@ -512,3 +512,38 @@ def test_tacaw_tiled_kernel_vs_generic(T, nx, ny, P):
     assert rel_l2(out[1][:, keep], ref[:, keep]) < 1e-4
     assert np.abs(out[1][:, dc]).max() <= 1e-6 * np.abs(ref).max() * T      # DC bin: rounding noise of the mean only
     assert np.array_equal(out[1], engine.tacaw_intensity(x).cpu().numpy())  # deterministic
+
+
+@pytest.mark.parametrize("box,grid", [((25.55, 25.55, 12.2), (256, 256)), ((51.15, 25.55, 3.1), (512, 256))])
+def test_phase_stack_equals_complex_stack(box, grid):
+    """The float32 phase format of the transmission stack (psb_build_phase / psb_propagate_phase: sigma*V stored,
+    exp(i*phase) evaluated inside the fused row pass) against the complex64 stack: exit waves of the same probes."""
+    from pyslice_b200 import _lib, engine, hostmath, synthetic
+    traj = synthetic.random_trajectory(n_atoms=900, box=box, n_frames=5, seed=23, types=(6, 14, 31), stray=True)
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    assert (plan.nx, plan.ny) == grid and engine.phase_format_supported(plan)
+    pos = dev(traj.positions)
+    t = engine.build_transmission(plan, pos)
+    ph = engine.build_transmission(plan, pos, phase=True)
+    assert ph.dtype == torch.float32 and ph.shape == t.shape
+    assert rel_l2(torch.polar(torch.ones_like(ph), ph).cpu().numpy(), t.cpu().numpy()) < 1e-6
+    g = torch.Generator(device="cuda").manual_seed(1)
+    probes = torch.randn((3,) + grid, generator=g, device="cuda", dtype=torch.float32).to(torch.complex64)
+    a = engine.propagate(plan, probes, t).clone()
+    b = engine.propagate(plan, probes, ph)
+    assert rel_l2(b.cpu().numpy(), a.cpu().numpy()) < 5e-6
+    # k-space output with layer taps goes through the same path
+    L = engine.layer_count(plan.nz, 4)
+    wa = torch.empty((L, 3, 5) + grid, dtype=torch.complex64, device="cuda")
+    wb = torch.empty_like(wa)
+    engine.propagate(plan, probes, t, wf_out=wa, layer_every=4)
+    engine.propagate(plan, probes, ph, wf_out=wb, layer_every=4)
+    assert rel_l2(wb.cpu().numpy(), wa.cpu().numpy()) < 5e-6
+    # grids without fused kernels refuse the format loudly
+    small = synthetic.random_trajectory(n_atoms=50, box=(6.35, 6.35, 2.1), n_frames=1, seed=1)
+    sxs, sys_, szs, *_ = hostmath.grid_from_box(small.box_matrix)
+    splan = engine.make_plan(sxs, sys_, szs, small.atom_types.tolist(), 100e3)
+    assert not engine.phase_format_supported(splan)
+    with pytest.raises(_lib.PsbError):
+        engine.build_transmission(splan, dev(small.positions), phase=True)
