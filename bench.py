@@ -303,7 +303,7 @@ def main():
             "clocks": clocks,
             "phases_ms_per_step": {"potential": pot_ms / args.steps, "propagate_incl_exit_fft": prop_ms / args.steps,
                                    "other_incl_tacaw": (ms_dev - pot_ms - prop_ms) / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "slice-step = fast_rows_kernel<256,0> + fast_cols_kernel<256,256,0> (psb_propagate)",
+            "roofline": {"bound": "hbm", "kernel": "slice-step = fast_rows_kernel<256,3> + fast_cols_kernel<256,256,0> (psb_propagate_phase)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
