@@ -42,18 +42,48 @@ def make_traj(wl, n_frames, frame0=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe), one sample per 200 ms:
-    every query takes driver locks that can hold up kernel launches for a few milliseconds."""
+    """SM clock and clock-event (throttle) reasons sampled during the timed region (B200_PROFILING.md recipe: the
+    nvidia-smi clocks line).  Primary source: NVML in-process (the library nvidia-smi itself reads), one light query per
+    100 ms from a thread; an `nvidia-smi -lms` child process was measured to stall this process's kernel launches for
+    1-15 ms per poll (and for up to 48 ms while it starts), which showed up as idle time in the device-timed arm only.
+    Fallback when NVML cannot be loaded: the nvidia-smi child, started before the warm-up."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.rows, self.proc, self.index, self.first = [], None, index, 0
+        self.nvml, self.handle, self.stop_flag, self.source = None, None, threading.Event(), None
+
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nvml = pynvml
+
+    def _nvml_loop(self):
+        n = self.nvml
+        masks = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)]
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self.stop_flag.is_set():
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append([sm, mx, 0.0] + ["Active" if bits & m else "Not Active" for _, m in masks])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
 
     def wait_ready(self, timeout=8.0):
-        """block until nvidia-smi delivered its first sample (its start-up is over)"""
+        """block until the first sample arrived (start-up of the source is over)"""
         t0 = time.time()
-        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+        while (self.proc is not None or self.nvml is not None) and not self.rows and time.time() - t0 < timeout:
             time.sleep(0.05)
 
     def mark(self):
@@ -62,9 +92,18 @@ class ClockSampler:
 
     def start(self):
         try:
+            self._nvml_open()
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -75,25 +114,29 @@ class ClockSampler:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.proc is None and self.nvml is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.th.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows[self.first:]:
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
+                    if str(v).lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
 def cpu_baseline(wl, seconds_target=20.0):

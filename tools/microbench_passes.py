@@ -18,7 +18,9 @@ plan = engine.make_plan(xs, xs, zs, [14], 100e3)
 probe = torch.ones((1, n, n), dtype=torch.complex64, device=dev)
 for F in batches:
     ph = torch.rand((F, nz, n, n), device=dev) * 6.28
-    t = torch.polar(torch.ones_like(ph), ph); del ph
+    # PSB_PHASE=1: the stack as float32 phases (single-probe format), else complex64 t
+    t = ph if os.environ.get("PSB_PHASE") == "1" else torch.polar(torch.ones_like(ph), ph)
+    del ph
     out = torch.empty((1, 1, F, n, n), dtype=torch.complex64, device=dev)
     work = torch.empty((F, n, n), dtype=torch.complex64, device=dev)
     for fast in ([True, False] if os.environ.get("PSB_AB", "1") == "1" else [True]):
