@@ -125,6 +125,10 @@ class ClockSampler:
                 self.proc.kill()
         else:
             self.th.join(timeout=2)
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows[self.first:]:
