@@ -116,10 +116,6 @@ __device__ __forceinline__ void pair_cis(cpx x, cpx& ea, cpx& eb) {
     eb = fast::c_make(cb, sb);
 }
 
-#ifdef PSB_NO_STCS
-#define __stcs(ptr, val) (*(ptr) = (val))
-#endif
-
 // exp(i*x) for one phase (R_STEP_PHASE): the scalar form of pair_cis
 __device__ __forceinline__ cpx cis1(float x) {
     float k = fmaf(x, 0.15915494309189535f, 12582912.f) - 12582912.f;
@@ -232,11 +228,7 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
     auto issue = [&](int unit, bool want_psi, bool want_t, int tb = 0) {
         if (want_psi) {
             mbar_expect_tx(mb_psi, C::kBytes);
-#ifdef PSB_NO_EVICT
-            if (false)
-#else
             if (MODE == R_TRANSMIT || MODE == R_PHASE)      // last use of the chunk's rows: do not let them displace the next chunk's
-#endif
                 bulk_g2s_hint(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi, stream_once);
             else
                 bulk_g2s(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi);
