@@ -41,94 +41,89 @@ def make_traj(wl, n_frames, frame0=0):
                                         displacement="phonon", frames=(frame0, frame0 + n_frames))
 
 
+_NVML_CHILD = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+try:
+    h = n.nvmlDeviceGetHandleByUUID(sys.argv[1]) if sys.argv[1].startswith("GPU-") else n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+except Exception:
+    h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
+mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+masks = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
+         n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
+while True:
+    sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+    bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+    print(",".join([str(sm), str(mx), "0"] + ["Active" if bits & m else "Not Active" for m in masks]), flush=True)
+    time.sleep(0.1)
+"""
+
+
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled during the timed region (B200_PROFILING.md recipe: the
-    nvidia-smi clocks line).  Primary source: NVML in-process (the library nvidia-smi itself reads), one light query per
-    100 ms from a thread; an `nvidia-smi -lms` child process was measured to stall this process's kernel launches for
-    1-15 ms per poll (and for up to 48 ms while it starts), which showed up as idle time in the device-timed arm only.
-    Fallback when NVML cannot be loaded: the nvidia-smi child, started before the warm-up."""
+    nvidia-smi clocks line).  Source: a child process reading the two values through NVML (the library nvidia-smi
+    itself reads) every 100 ms.  An `nvidia-smi -lms` child was measured to stall this process's kernel launches for
+    1-15 ms per poll (up to 48 ms while it starts), which showed up as idle time in the device-timed arm; NVML loaded
+    into this process made the end-to-end arm that follows noisier.  Fallback when pynvml is missing: nvidia-smi.
+    Either child is started before the warm-up; only samples taken during the timed region are reported."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index, self.first = [], None, index, 0
-        self.nvml, self.handle, self.stop_flag, self.source = None, None, threading.Event(), None
+        self.rows, self.proc, self.index, self.first, self.source = [], None, index, 0, None
 
-    def _nvml_open(self):
-        import pynvml
-        pynvml.nvmlInit()
+    def _spawn(self, cmd, source):
+        self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.source = source
+        self.th = threading.Thread(target=self._read, args=(self.proc,), daemon=True)
+        self.th.start()
+
+    def start(self):
         try:
-            import torch
-            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
-            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
-            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
-        except Exception:
-            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-        self.nvml = pynvml
-
-    def _nvml_loop(self):
-        n = self.nvml
-        masks = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
-                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)]
-        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
-        while not self.stop_flag.is_set():
+            uuid = ""
             try:
-                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-                bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-                self.rows.append([sm, mx, 0.0] + ["Active" if bits & m else "Not Active" for _, m in masks])
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
             except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+                uuid = str(self.index)
+            self._spawn([sys.executable, "-c", _NVML_CHILD, uuid, str(self.index)], "nvml")
+        except Exception:
+            self.proc = None
+
+    def _start_smi(self):
+        try:
+            self._spawn(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                         "-lms", "200"], "nvidia-smi")
+        except Exception:
+            self.proc = None
 
     def wait_ready(self, timeout=8.0):
-        """block until the first sample arrived (start-up of the source is over)"""
+        """block until the first sample arrived (start-up of the child is over); a child that died without one
+        (no pynvml) is replaced by nvidia-smi"""
         t0 = time.time()
-        while (self.proc is not None or self.nvml is not None) and not self.rows and time.time() - t0 < timeout:
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            if self.proc.poll() is not None and self.source == "nvml" and not self.rows:
+                self._start_smi()
             time.sleep(0.05)
 
     def mark(self):
         """the timed region starts here: earlier samples (warm-up) are not reported"""
         self.first = len(self.rows)
 
-    def start(self):
-        try:
-            self._nvml_open()
-            self.source = "nvml"
-            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
-            self.th.start()
-            return
-        except Exception:
-            self.nvml = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.source = "nvidia-smi"
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
+    def _read(self, proc):
+        for line in proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc is None and self.nvml is None:
+        if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
-        self.stop_flag.set()
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        else:
-            self.th.join(timeout=2)
-            try:
-                self.nvml.nvmlShutdown()
-            except Exception:
-                pass
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows[self.first:]:

@@ -256,7 +256,7 @@ int psb_phase_format_supported(int nx, int ny) {
 int psb_transmission_from_potential(const float* v, psb_c64* t, long long n, float sigma, void* stream) {
     if (!v || !t || n < 0) return fail(PSB_ERR_INVALID, "psb_transmission_from_potential: bad argument");
     if (n == 0) return PSB_OK;
-    TransmitParams p{v, f2(t), n, sigma};
+    TransmitParams p{v, f2(t), n, sigma, n, n};
     long long blocks = (n + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     return go<Transmit>(dim3((unsigned)blocks), 0, as_stream(stream), p, "transmit");
@@ -348,10 +348,12 @@ static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* 
 #endif
     if (phase) {
         if (!fast) return fail(PSB_ERR_UNSUPPORTED, "psb_propagate_phase: the phase format needs a grid with fused kernels");
-        for (int f = 0; f < n_frames; ++f) {        // slice 0 of every frame as t for the generic first pass
-            int rc0 = psb_transmission_from_potential(phase + (long long)f * nz * img, t0 + (long long)f * img, img, 1.0f, stream);
-            if (rc0 != PSB_OK) return rc0;
-        }
+        // slice 0 of every frame as t for the generic first pass (one strided launch)
+        TransmitParams tp{phase, f2(t0), (long long)n_frames * img, 1.0f, img, (long long)nz * img};
+        long long blocks = (tp.n + 255) / 256;
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        int rc0 = go<Transmit>(dim3((unsigned)blocks), 0, s, tp, "transmit");
+        if (rc0 != PSB_OK) return rc0;
         row.mul_img_stride = img;
     }
     int layer = 0;

@@ -361,11 +361,14 @@ struct StructureFactorPaired {
 };
 
 // t = exp(i*sigma*V) from a real potential (for Propagate() on a user-supplied Potential object)
+// n elements in blocks of `block` contiguous ones: block b of V starts at b * v_block_stride, of t at b * block
+// (block = n, one block: a plain array; block = one image, v_block_stride = one frame's stack: slice 0 of every frame)
 struct TransmitParams {
     const float* V;
     float2* t;
     long long n;
     float sigma;
+    long long block, v_block_stride;
 };
 struct Transmit {
     static constexpr int kThreads = 256;
@@ -373,8 +376,9 @@ struct Transmit {
     template <class Ctx>
     static PSB_D void run(const Ctx& cx, const TransmitParams& p) {
         for (long long i = (long long)cx.bx() * kThreads + cx.tid(); i < p.n; i += (long long)cx.gx() * kThreads) {
+            const long long b = i / p.block;
             float s, c;
-            sincosf(p.sigma * p.V[i], &s, &c);
+            sincosf(p.sigma * p.V[b * p.v_block_stride + (i - b * p.block)], &s, &c);
             p.t[i] = make_float2(c, s);
         }
     }
