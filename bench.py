@@ -56,14 +56,14 @@ while True:
     sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
     bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
     print(",".join([str(sm), str(mx), "0"] + ["Active" if bits & m else "Not Active" for m in masks]), flush=True)
-    time.sleep(0.25)
+    time.sleep(0.2)
 """
 
 
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled during the timed region (B200_PROFILING.md recipe: the
     nvidia-smi clocks line).  Source: a child process reading the two values through NVML (the library nvidia-smi
-    itself reads) every 250 ms (each poll from another process can hold up this process's kernel launches for a few
+    itself reads) every 200 ms (each poll from another process can hold up this process's kernel launches for a few
     milliseconds: fewer polls, less idle time in the device-timed arm).  An `nvidia-smi -lms` child was measured to stall this process's kernel launches for
     1-15 ms per poll (up to 48 ms while it starts), which showed up as idle time in the device-timed arm; NVML loaded
     into this process made the end-to-end arm that follows noisier.  Fallback when pynvml is missing: nvidia-smi.
