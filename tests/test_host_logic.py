@@ -73,3 +73,22 @@ def test_synthetic_grids_hit_requested_sizes():
     t = synthetic.hbn_graphene_trajectory(n_frames=1)
     xs, ys, zs, *_ = hostmath.grid_from_box(t.box_matrix)
     assert (len(xs), len(ys), len(zs)) == (512, 512, 67) and t.n_atoms == 9600
+
+
+def test_batch_and_chunk_sizing_rules(monkeypatch):
+    """engine._fewest_rounds / chunk_images: host-side sizing against the persistent grids (296 CTA slots on 148 SMs)"""
+    from types import SimpleNamespace as NS
+
+    from pyslice_b200 import engine
+    monkeypatch.setattr(engine, "_sm_count", lambda: 148)
+    # C2: 500 frames of one 256 x 256 probe (16 column tiles per image): 127 per batch = 3 x 7 + 7 rounds
+    fb = engine._fewest_rounds(500, 127, 16, 296)
+    rounds = lambda fb: (500 // fb) * -(-fb * 16 // 296) + (-(-(500 % fb) * 16 // 296) if 500 % fb else 0)
+    assert rounds(fb) == 28 and rounds(100) == 30 and fb <= 127
+    assert engine._fewest_rounds(3, 3, 16, 296) == 3 and engine._fewest_rounds(100, 1, 64, 296) == 1
+    # potential chunks: as many images as the scratch holds, nudged only on large grids
+    assert engine.chunk_images(NS(nx=256, ny=256, nz=512), 100) == 128
+    assert engine.chunk_images(NS(nx=512, ny=512, nz=67), 100) == 32
+    assert engine.chunk_images(NS(nx=1024, ny=1024, nz=123), 100) == 9          # 1152 tiles = 3.9 rounds, not 8 -> 3.5 of 4
+    assert engine.chunk_images(NS(nx=256, ny=256, nz=9), 2) == 10                # never more than the work there is
+    assert engine.chunk_images(NS(nx=4096, ny=4096, nz=40), 1) == 1
