@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the multislice + TACAW hot path (BASELINE.json metric: slice-steps/s).
 
-    python bench.py --gpus 1 --steps 3 --warmup 3
+    python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
     python bench.py --impl reference ...     # the CPU port of the reference path (oracle), all host threads
 
@@ -41,90 +41,96 @@ def make_traj(wl, n_frames, frame0=0):
                                         displacement="phonon", frames=(frame0, frame0 + n_frames))
 
 
-_NVML_CHILD = r"""
-import sys, time
-import pynvml as n
-n.nvmlInit()
-try:
-    h = n.nvmlDeviceGetHandleByUUID(sys.argv[1]) if sys.argv[1].startswith("GPU-") else n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
-except Exception:
-    h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[2]))
-mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
-masks = [n.nvmlClocksEventReasonHwSlowdown, n.nvmlClocksEventReasonHwThermalSlowdown,
-         n.nvmlClocksEventReasonSwThermalSlowdown, n.nvmlClocksEventReasonSwPowerCap]
-while True:
-    sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
-    bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
-    print(",".join([str(sm), str(mx), "0"] + ["Active" if bits & m else "Not Active" for m in masks]), flush=True)
-    time.sleep(0.2)
-"""
-
-
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled during the timed region (B200_PROFILING.md recipe: the
-    nvidia-smi clocks line).  Source: a child process reading the two values through NVML (the library nvidia-smi
-    itself reads) every 200 ms (each poll from another process can hold up this process's kernel launches for a few
-    milliseconds: fewer polls, less idle time in the device-timed arm).  An `nvidia-smi -lms` child was measured to stall this process's kernel launches for
-    1-15 ms per poll (up to 48 ms while it starts), which showed up as idle time in the device-timed arm; NVML loaded
-    into this process made the end-to-end arm that follows noisier.  Fallback when pynvml is missing: nvidia-smi.
-    Either child is started before the warm-up; only samples taken during the timed region are reported."""
+    nvidia-smi clocks line).  Source: NVML loaded into this process (the library nvidia-smi itself reads), one light
+    query per 100 ms from a thread.  Any poller in ANOTHER process -- `nvidia-smi -lms` or an NVML child, at 100 to
+    250 ms -- was measured to hold up this process's kernel launches at random, 1-17 ms of idle time per step in the
+    device-timed arm (48 ms while nvidia-smi starts); the in-process thread does not.  Because runs with NVML loaded
+    showed a noisier end-to-end arm, that arm is timed FIRST, before NVML is touched.
+    Fallback when NVML cannot be loaded: an nvidia-smi child, started before the warm-up."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index, self.first, self.source = [], None, index, 0, None
+        self.rows, self.proc, self.index, self.first = [], None, index, 0
+        self.nvml, self.handle, self.stop_flag, self.source = None, None, threading.Event(), None
 
-    def _spawn(self, cmd, source):
-        self.proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        self.source = source
-        self.th = threading.Thread(target=self._read, args=(self.proc,), daemon=True)
-        self.th.start()
-
-    def start(self):
+    def _nvml_open(self):
+        import pynvml
+        pynvml.nvmlInit()
         try:
-            uuid = ""
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        self.nvml = pynvml
+
+    def _nvml_loop(self):
+        n = self.nvml
+        masks = [("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown), ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                 ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown), ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)]
+        mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self.stop_flag.is_set():
             try:
-                import torch
-                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
-                uuid = uuid if uuid.startswith("GPU-") else "GPU-" + uuid
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                bits = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                self.rows.append([sm, mx, 0.0] + ["Active" if bits & m else "Not Active" for _, m in masks])
             except Exception:
-                uuid = str(self.index)
-            self._spawn([sys.executable, "-c", _NVML_CHILD, uuid, str(self.index)], "nvml")
-        except Exception:
-            self.proc = None
-
-    def _start_smi(self):
-        try:
-            self._spawn(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                         "-lms", "200"], "nvidia-smi")
-        except Exception:
-            self.proc = None
+                pass
+            self.stop_flag.wait(0.1)
 
     def wait_ready(self, timeout=8.0):
-        """block until the first sample arrived (start-up of the child is over); a child that died without one
-        (no pynvml) is replaced by nvidia-smi"""
+        """block until the first sample arrived (start-up of the source is over)"""
         t0 = time.time()
-        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
-            if self.proc.poll() is not None and self.source == "nvml" and not self.rows:
-                self._start_smi()
+        while (self.proc is not None or self.nvml is not None) and not self.rows and time.time() - t0 < timeout:
             time.sleep(0.05)
 
     def mark(self):
         """the timed region starts here: earlier samples (warm-up) are not reported"""
         self.first = len(self.rows)
 
-    def _read(self, proc):
-        for line in proc.stdout:
+    def start(self):
+        try:
+            self._nvml_open()
+            self.source = "nvml"
+            self.th = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvidia-smi"
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def stop(self):
-        if self.proc is None:
+        if self.proc is None and self.nvml is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        self.stop_flag.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        else:
+            self.th.join(timeout=2)
+            try:
+                self.nvml.nvmlShutdown()
+            except Exception:
+                pass
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows[self.first:]:
@@ -182,7 +188,7 @@ def run_reference(args, wl, name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT, choices=list(WORKLOADS))
@@ -238,6 +244,30 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---------------- arm 2 (timed first, see ClockSampler): end to end through the public API with host buffers ----
+    pinned = torch.empty(local_traj.positions.shape, dtype=torch.float64).pin_memory()
+    pinned.numpy()[...] = local_traj.positions
+    host_traj = Trajectory(local_traj.atom_types, pinned.numpy(), np.zeros((F, A, 3)), local_traj.box_matrix,
+                           local_traj.timestep)
+    rows = nx // world + (1 if rank < nx % world else 0)
+    out_host = torch.empty((1, T_total, rows, ny), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        c = setup_calc(host_traj)
+        wf = c.run()
+        tac = TACAWData(wf)
+        out_host.copy_(tac.intensity, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+
     # ---------------- arm 1: inputs resident in HBM ------------------------------------------
     pos_dev = torch.from_numpy(local_traj.positions).to(dev)
     dev_traj = Trajectory.__new__(Trajectory)
@@ -252,8 +282,7 @@ def main():
         tac = TACAWData(wf)
         return tac
 
-    # nvidia-smi is started BEFORE the warm-up: its start-up (NVML initialisation, device enumeration) takes driver
-    # locks that stall kernel launches for tens of milliseconds when it lands inside the timed region; only the
+    # the clock sampler is started BEFORE the warm-up (its start-up must not land inside the timed region); only the
     # samples taken during the timed region are reported
     sampler = ClockSampler(local)
     if rank == 0:
@@ -277,30 +306,6 @@ def main():
     spectrum = tac.spectrum()          # touches the result (and checks the reducers run)
     assert np.isfinite(spectrum).all()
     del tac
-
-    # ---------------- arm 2: end to end through the public API with host buffers -------------
-    pinned = torch.empty(local_traj.positions.shape, dtype=torch.float64).pin_memory()
-    pinned.numpy()[...] = local_traj.positions
-    host_traj = Trajectory(local_traj.atom_types, pinned.numpy(), np.zeros((F, A, 3)), local_traj.box_matrix,
-                           local_traj.timestep)
-    rows = nx // world + (1 if rank < nx % world else 0)
-    out_host = torch.empty((1, T_total, rows, ny), dtype=torch.float32).pin_memory()
-
-    def e2e_step():
-        c = setup_calc(host_traj)
-        wf = c.run()
-        tac = TACAWData(wf)
-        out_host.copy_(tac.intensity, non_blocking=True)
-        torch.cuda.synchronize()
-
-    for _ in range(max(1, args.warmup // 2)):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    ms_e2e = (time.perf_counter() - t0) * 1e3
 
     if world > 1:
         t = torch.tensor([ms_dev, ms_e2e, phases.get("propagate", 0.0), phases.get("potential", 0.0)],

@@ -233,13 +233,16 @@ class MultisliceCalculator:
         f_lo, f_hi = self._local_frames()
         T_loc = f_hi - f_lo
         P, nx, ny = self.n_probes, self.nx, self.ny
-        store = torch.empty((self.n_layers, P, T_loc, nx, ny), dtype=torch.complex64, device=self.device)
         fb, pb = engine.batch_sizes(plan, P, max(T_loc, 1))
-        work = torch.empty((fb * min(pb, P), nx, ny), dtype=torch.complex64, device=self.device)
         # one probe per frame: the stack is written once and read once, so it is kept as float32 phases (half the HBM
         # traffic, exp(i*phase) evaluated inside the fused slice step); shared by several probes it stays complex64
         use_phase = P == 1 and engine.phase_format_supported(plan)
         tbuf = torch.empty((fb, plan.nz, nx, ny), dtype=torch.float32 if use_phase else torch.complex64, device=self.device)
+        work = torch.empty((fb * min(pb, P), nx, ny), dtype=torch.complex64, device=self.device)
+        # the result store is allocated AFTER the multi-GB stack: while a previous result is still alive the caching
+        # allocator would otherwise carve the new store out of the cached stack block and then cudaMalloc a fresh stack
+        # (tens of milliseconds of idle GPU, seen as random gaps between the phases of repeated runs)
+        store = torch.empty((self.n_layers, P, T_loc, nx, ny), dtype=torch.complex64, device=self.device)
         positions = self.trajectory.positions
         # frame cache (opt-in): cached frames are loaded, the others are computed in contiguous runs and handed to
         # a writer thread (D2H on a side stream would buy nothing here: the files are written by the host anyway)
