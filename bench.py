@@ -44,7 +44,8 @@ def make_traj(wl, n_frames, frame0=0):
 class ClockSampler:
     """SM clock and clock-event (throttle) reasons sampled during the timed region (B200_PROFILING.md recipe: the
     nvidia-smi clocks line).  Source: NVML loaded into this process (the library nvidia-smi itself reads), one light
-    query per 100 ms from a thread.  Any poller in ANOTHER process -- `nvidia-smi -lms` or an NVML child, at 100 to
+    query per 400 ms from a thread plus one when the timed region opens (each query can hold a driver lock that kernel
+    launches of this process also take: 17 polls at 100 ms cost a 10-step run ~10 ms of idle GPU per step).  Any poller in ANOTHER process -- `nvidia-smi -lms` or an NVML child, at 100 to
     250 ms -- was measured to hold up this process's kernel launches at random, 1-17 ms of idle time per step in the
     device-timed arm (48 ms while nvidia-smi starts); the in-process thread does not.  Because runs with NVML loaded
     showed a noisier end-to-end arm, that arm is timed FIRST, before NVML is touched.
@@ -55,6 +56,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc, self.index, self.first = [], None, index, 0
         self.nvml, self.handle, self.stop_flag, self.source = None, None, threading.Event(), None
+        self.wake = threading.Event()
 
     def _nvml_open(self):
         import pynvml
@@ -80,7 +82,8 @@ class ClockSampler:
                 self.rows.append([sm, mx, 0.0] + ["Active" if bits & m else "Not Active" for _, m in masks])
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.wake.wait(0.4)          # every 400 ms, and at once when mark() opens the timed region
+            self.wake.clear()
 
     def wait_ready(self, timeout=8.0):
         """block until the first sample arrived (start-up of the source is over)"""
@@ -91,6 +94,7 @@ class ClockSampler:
     def mark(self):
         """the timed region starts here: earlier samples (warm-up) are not reported"""
         self.first = len(self.rows)
+        self.wake.set()
 
     def start(self):
         try:
@@ -119,6 +123,7 @@ class ClockSampler:
         if self.proc is None and self.nvml is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"]}
         self.stop_flag.set()
+        self.wake.set()
         if self.proc is not None:
             self.proc.terminate()
             try:
