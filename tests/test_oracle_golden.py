@@ -115,3 +115,48 @@ def test_si_c1_frame0():
     psi = orc.propagate(np.ones((256, 256)), V, xs, ys, zs, 100e3, workers=4)
     wf = orc.exit_to_kspace(psi)[0]
     assert rel_l2(wf, g["wf"]) < 1e-6                                   # complex64 golden
+
+
+# ---- the oracle against the reference's unit-test recipes (tests/golden/recipes.npz, produced by the reference's code) --
+
+def _dz(ary, previous):
+    F, D = np.absolute(np.asarray(ary, dtype=np.complex128)), np.absolute(np.asarray(previous, dtype=np.complex128))
+    return np.sum((F - D) ** 2) / np.sum(F ** 2)
+
+
+def test_oracle_replays_reference_recipes_01_02_05():
+    """01_potentials.py, 02_propagate.py, 05_tacaw.py with the oracle on the recipes' seeded trajectory, under the
+    recipes' own residual (float32 storage of the goldens bounds it at ~1e-14)"""
+    from tests.recipes_input import recipe_trajectory
+    g = golden("recipes.npz")
+    traj = recipe_trajectory()
+    xs, ys, zs, lx, ly, lz = orc.grid_from_box(traj.box_matrix)
+    V = orc.potential(xs, ys, zs, traj.positions[0], traj.atom_types, workers=4)
+    assert V.shape == (154, 171, 14)
+    assert _dz(V[::3, ::3, :], g["r01_potential"]) < 1e-12
+    probe = orc.probe_array(xs, ys, 5, 100e3)
+    exit_wave = orc.propagate(probe, V, xs, ys, zs, 100e3, workers=4)[0]
+    assert _dz(exit_wave[::2, ::2], g["r02_exit"]) < 1e-12
+    assert np.linalg.norm(exit_wave[::2, ::2] - g["r02_exit"]) / np.linalg.norm(g["r02_exit"]) < 1e-6
+    wf, _ = orc.multislice_run(traj.positions, traj.atom_types, traj.box_matrix, aperture=0.0, voltage_eV=100e3, workers=4)
+    inten, freqs = orc.tacaw_intensity(wf[..., 0], np.arange(traj.n_frames) * traj.timestep)
+    assert np.allclose(freqs, g["r05_frequencies"], rtol=0, atol=1e-9)
+    assert _dz(inten[0, 7] ** .1, g["r05_slice"]) < 1e-10
+    keep = [i for i in range(12) if i != 6]
+    assert np.abs(orc.spectrum(inten)[keep] / g["r05_spectrum"][keep] - 1).max() < 1e-9
+
+
+def test_oracle_replays_reference_recipe_04_haadf():
+    """04_haadf.py: cropped trajectory, 3 shuffled frames, 14 x 16 probe grid at 30 mrad, calculateADF"""
+    from pyslice_b200.multislice.multislice import probe_grid
+    from tests.recipes_input import A, B, recipe_trajectory
+    g = golden("recipes.npz")
+    cut = recipe_trajectory().slice_positions([0, 4 * A], [0, 3 * B])
+    three = cut.slice_timesteps(g["r04_frames"])
+    xy = probe_grid([A, 3 * A], [B, 2 * B], 14, 16)
+    wf, grid = orc.multislice_run(three.positions, three.atom_types, three.box_matrix, aperture=30.0, voltage_eV=100e3,
+                                  probe_positions=[tuple(p) for p in xy], workers=4)
+    kxs, kys, _ = orc.wf_axes(wf.shape[2], wf.shape[3], 0.1, three.n_frames, three.timestep)
+    adf, ux, uy = orc.haadf_adf(wf, kxs, kys, xy, 100e3)
+    assert adf.shape == (14, 16)
+    assert np.abs(adf / g["r04_adf"] - 1).max() < 1e-5
