@@ -3,21 +3,25 @@
 
     python bench.py --gpus 1 --steps 10 --warmup 3
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
-    python bench.py --impl reference ...     # the CPU port of the reference path (oracle), all host threads
+    python bench.py --impl reference ...     # the UNMODIFIED reference (torch CPU path) from baseline/_ref
 
-Workload (config C2 of BASELINE.json): plane-wave TACAW on 10 000-atom Si, 256 x 256 grid, 512 slices,
+Default workload = config C2 of BASELINE.json: plane-wave TACAW on 10 000-atom Si, 256 x 256 grid, 512 slices,
 500 MD frames per GPU (weak scaling: frames are sharded by rank), full time-axis FFT to the THz spectrum.
+`--workload` selects the other configurations (C1, C3, C4 = strong scaling over 2 000 frames, C5).
 One "step" = potential build + propagation of every frame + exit FFT + [all-to-all] + TACAW time FFT.
 
 The JSON line carries: value (inputs resident in HBM), e2e (public API with pinned-host inputs, H2D and
-D2H inside the timed region), roofline of the slice-step kernels, cpu_baseline (oracle on host cores),
-clocks sampled during the timed region and the number of kernels this library launched.
+D2H inside the timed region), roofline of the slice-step kernels (+ the fp32-pipe floor of the same kernels),
+cpu_baseline (the reference's torch path on the host cores, and the NumPy port beside it), clocks sampled during the
+timed region, the number of kernels this library launched and -- on more than one GPU -- the outcome of the
+N-GPU == 1-GPU parity check run before the warm-up.
 """
 import argparse
 import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -27,18 +31,45 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (cells, lattice a, frames per GPU, grid, slices)
-    "c2_si_256x256x512_500f_planewave": dict(cells=(5, 5, 50), a=5.11, frames=500, grid=(256, 256, 512), seed=1),
-    "c1_si_256x256x103_20f_planewave": dict(cells=(5, 5, 10), a=5.11, frames=20, grid=(256, 256, 103), seed=0),
+    # frames: per GPU for "weak" scaling, in total for "strong"; probes = n -> n x n probe_grid over the central half of the box
+    "c2_si_256x256x512_500f_planewave": dict(sample="si", cells=(5, 5, 50), a=5.11, frames=500, grid=(256, 256, 512), seed=1,
+                                             probes=0, aperture=0.0, layer_every=0, scaling="weak"),
+    "c1_si_256x256x103_20f_planewave": dict(sample="si", cells=(5, 5, 10), a=5.11, frames=20, grid=(256, 256, 103), seed=0,
+                                            probes=0, aperture=0.0, layer_every=0, scaling="weak"),
+    "c3_hbn_512x512x67_100f_16x16": dict(sample="hbn", frames=100, grid=(512, 512, 67), seed=2, probes=16, aperture=30.0,
+                                         layer_every=0, scaling="weak"),
+    "c4_si_1024x1024x123_2000f_planewave": dict(sample="si", cells=(20, 20, 12), a=5.1175, frames=2000, grid=(1024, 1024, 123),
+                                                seed=3, probes=0, aperture=0.0, layer_every=0, scaling="strong"),
+    # C5 = 500 frames x 64 probes x 7 layers x 2 MB = 470 GB of exit waves: 63 frames (an eighth) per GPU
+    "c5_hbn_512x512x67_63f_8x8_layers10": dict(sample="hbn", frames=63, grid=(512, 512, 67), seed=4, probes=8, aperture=30.0,
+                                               layer_every=10, scaling="weak"),
 }
+ALIASES = {"c1": "c1_si_256x256x103_20f_planewave", "c2": "c2_si_256x256x512_500f_planewave",
+           "c3": "c3_hbn_512x512x67_100f_16x16", "c4": "c4_si_1024x1024x123_2000f_planewave",
+           "c5": "c5_hbn_512x512x67_63f_8x8_layers10"}
 DEFAULT = "c2_si_256x256x512_500f_planewave"
 VOLTAGE = 100e3
+
+# fp32-pipe floor of the fused slice step: lane-cycles per pixel and slice step of the packed radix-16
+# transforms + pointwise multiplies, by line length (both passes; 1024-point lines: radix 16 x 4 x 16)
+FP32_LANE_CYCLES_PER_PIXEL = {256: 112.0, 512: 129.0, 1024: 141.0}
 
 
 def make_traj(wl, n_frames, frame0=0):
     from pyslice_b200 import synthetic
+    if wl["sample"] == "hbn":
+        return synthetic.hbn_graphene_trajectory(n_frames=n_frames, seed=wl["seed"], frames=(frame0, frame0 + n_frames))
     return synthetic.silicon_trajectory(cells=wl["cells"], a=wl["a"], n_frames=n_frames, seed=wl["seed"],
                                         displacement="phonon", frames=(frame0, frame0 + n_frames))
+
+
+def probe_positions(wl, box_matrix):
+    if not wl["probes"]:
+        return None
+    from pyslice_b200.multislice.multislice import probe_grid
+    lx, ly = box_matrix[0, 0], box_matrix[1, 1]
+    n = wl["probes"]
+    return [tuple(p) for p in probe_grid([0.25 * lx, 0.75 * lx], [0.25 * ly, 0.75 * ly], n, n)]
 
 
 class ClockSampler:
@@ -150,51 +181,208 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": self.source}
 
 
-def cpu_baseline(wl, z_fraction=1.0):
-    """The oracle (NumPy/SciPy port of the reference's torch path, float64) on the host cores: a bounded
-    sample of the same workload -- `cores` frames in parallel threads, full slice stack each (z_fraction < 1: a
-    thinner sample of the same crystal, for runs of many reference steps; the rate per slice-step is unchanged)."""
+# ---- CPU arms ------------------------------------------------------------------------------------------------------
+def reference_root():
+    """where the unmodified reference lives: baseline/_ref (tools/install_reference.py; travels to the GPU box), else the
+    build container's checkout"""
+    for cand in (os.path.join(ROOT, "baseline", "_ref"), os.environ.get("PYSLICE_REFERENCE", "/root/reference")):
+        if os.path.exists(os.path.join(cand, "src", "multislice", "calculators.py")) and os.path.exists(os.path.join(cand, "kirkland.txt")):
+            return cand
+    return None
+
+
+def reference_sample_frames(wl):
+    """frames of the bounded sample: ~10-30 s of the reference's CPU work (it takes 1-2 s per plane-wave frame at 256^2 x 512
+    on 16 threads, ~20 s per frame at 1024^2, ~1 s per probe and frame at 512^2 x 67)"""
+    nx = wl["grid"][0]
+    if wl["probes"]:
+        return 1
+    return 6 if nx <= 256 else (2 if nx <= 512 else 1)
+
+
+def reference_torch_step(wl, name, n_frames=None, n_probes_cap=16):
+    """One bounded sample of the workload through the REFERENCE ITSELF: MultisliceCalculator(force_cpu=True).setup().run()
+    (reference src/multislice/calculators.py:41,96,163) + TACAWData (src/postprocessing/tacaw_data.py:38), full slice
+    stack, all host threads torch can use, fresh temp cwd (its frame cache key ignores the positions).
+    Returns (slice-steps/s, description dict) or raises when the reference is not installed."""
+    import torch
+    root = reference_root()
+    if root is None:
+        raise RuntimeError("reference not installed: run tools/install_reference.py in the build container")
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from src.multislice.calculators import MultisliceCalculator as RefCalc        # noqa: E402  (the reference's modules)
+    from src.multislice.trajectory import Trajectory as RefTraj                   # noqa: E402
+    from src.postprocessing.tacaw_data import TACAWData as RefTACAW               # noqa: E402
+    import logging
+    logging.getLogger("src.multislice.calculators").setLevel(logging.WARNING)
+    cores = os.cpu_count() or 1
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    torch.set_num_threads(cores)
+    n = n_frames or reference_sample_frames(wl)
+    traj = make_traj(wl, max(n, 2))            # TACAWData needs two time points for its frequency axis
+    n = traj.n_frames
+    pp = probe_positions(wl, traj.box_matrix)
+    if pp is not None and len(pp) > n_probes_cap:
+        pp = pp[:: len(pp) // n_probes_cap][:n_probes_cap]
+    P = len(pp) if pp is not None else 1
+    ref_traj = RefTraj(atom_types=traj.atom_types, positions=traj.positions, velocities=traj.velocities,
+                       box_matrix=traj.box_matrix, timestep=traj.timestep)
+    cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="pyslice_ref_")
+    os.chdir(tmp)
+    try:
+        t0 = time.perf_counter()
+        calc = RefCalc(force_cpu=True)
+        calc.setup(ref_traj, aperture=wl["aperture"], voltage_eV=VOLTAGE, probe_positions=pp)      # cleanup_temp_files=True hits a NameError in the reference (calculators.py:237)
+        wf = calc.run()
+        t1 = time.perf_counter()
+        tac = RefTACAW(wf)
+        _ = tac.spectrum()
+        t2 = time.perf_counter()
+    finally:
+        os.chdir(cwd)
+        import shutil
+        shutil.rmtree(tmp, ignore_errors=True)
+    nz = calc.nz
+    assert (calc.nx, calc.ny, nz) == tuple(wl["grid"]), (calc.nx, calc.ny, nz)
+    steps = P * n * nz
+    dt = t2 - t0
+    return steps / dt, {
+        "value": steps / dt, "unit": "slice-steps/s", "cores": cores, "kind": "reference",
+        "impl": "reference-torch: unmodified h-walk/PySlice MultisliceCalculator(force_cpu=True).setup().run() + TACAWData, "
+                "torch CPU complex128, imported from " + os.path.relpath(root, ROOT),
+        "sample": f"{n} of {wl['frames']} frames, {P} probe(s), all {nz} slices of workload {name}: run() {t1 - t0:.1f} s "
+                  f"+ TACAWData/spectrum {t2 - t1:.2f} s, torch.set_num_threads({cores})",
+        "slice_steps_in_sample": steps, "seconds": dt, "torch_threads": cores}
+
+
+def port_step(wl, z_fraction=1.0):
+    """The oracle (NumPy/SciPy port of the reference's torch path, float64) on the host cores: reported beside the
+    reference's own figure as a second, labelled baseline (it is the faster of the two)."""
     from oracle import pyslice_oracle as orc
     cores = os.cpu_count() or 1
-    n = max(1, min(cores, 16))
-    cz = max(2, int(round(wl["cells"][2] * z_fraction)))
-    thin = dict(wl, cells=(wl["cells"][0], wl["cells"][1], cz))
+    n = max(2, min(cores, 16))
+    cz = max(2, int(round(wl["cells"][2] * z_fraction))) if wl["sample"] == "si" else None
+    thin = dict(wl, cells=(wl["cells"][0], wl["cells"][1], cz)) if cz else wl
     traj = make_traj(thin, n)
+    pp = probe_positions(wl, traj.box_matrix)
+    if pp is not None:
+        pp = pp[:: max(1, len(pp) // 4)][:4]
     t0 = time.time()
-    wf, grid = orc.multislice_run(traj.positions, traj.atom_types, traj.box_matrix, aperture=0.0, voltage_eV=VOLTAGE,
-                                  frame_threads=n, workers=1)
-    inten, _ = orc.tacaw_intensity(wf[..., 0], np.arange(n) * traj.timestep) if n > 1 else (None, None)
+    wf, grid = orc.multislice_run(traj.positions, traj.atom_types, traj.box_matrix, aperture=wl["aperture"], voltage_eV=VOLTAGE,
+                                  probe_positions=pp, frame_threads=n, workers=1)
+    orc.tacaw_intensity(wf[..., 0], np.arange(n) * traj.timestep)
     dt = time.time() - t0
     nz = len(grid["zs"])
-    return {"value": n * nz / dt, "unit": "slice-steps/s", "cores": n, "kind": "port", "slices": nz,
-            "sample": f"{n} of {wl['frames']} frames ({nz} of {wl['grid'][2]} slices, potential + propagation + exit FFT + TACAW), "
-                      f"{n} frame threads, float64, {dt:.1f} s"}
+    P = wf.shape[0]
+    return {"value": P * n * nz / dt, "unit": "slice-steps/s", "cores": n, "kind": "port",
+            "sample": f"{n} frames x {P} probe(s) x {nz} slices, {n} frame threads, NumPy/SciPy float64, {dt:.1f} s"}
+
+
+def cpu_baseline(wl, name):
+    """cpu_baseline object of the GPU arm's line (rank 0, N = 1): the reference's torch path on a bounded sample; the
+    NumPy port as a second figure under "port"."""
+    try:
+        _, base = reference_torch_step(wl, name)
+    except Exception as e:                                     # reference tree absent: the port is all there is
+        base = port_step(wl)
+        base["note"] = f"reference not runnable here ({type(e).__name__}: {e}); NumPy port instead"
+        return base
+    try:
+        base["port"] = port_step(wl, z_fraction=0.25)
+    except Exception as e:                                     # pragma: no cover
+        base["port"] = {"error": str(e)}
+    return base
+
+
+L2_NOTE = ("GPU arm: inputs larger than L2, no explicit flush -- every timed step streams the positions and a multi-GB "
+           "transmission stack per frame batch through HBM; only the psi batch (<= 80 MB) is L2-resident by design")
+
+
+def config_block(wl, name, world, counts, A, P):
+    """the `config` object, identical in the GPU arm and the reference arm of one invocation"""
+    nx, ny, nz = wl["grid"]
+    return {"workload": name, "grid": [nx, ny, nz], "atoms": A, "frames_per_gpu": max(counts), "frames_total": sum(counts),
+            "probes": P, "aperture_mrad": wl["aperture"], "layer_every": wl["layer_every"], "voltage_eV": VOLTAGE,
+            "parallelism": f"frames sharded over {world} GPU(s), all-to-all to kx rows", "l2": L2_NOTE}
+
+
+def frame_counts(wl, world):
+    if wl["scaling"] == "strong":
+        return [wl["frames"] // world + (1 if r < wl["frames"] % world else 0) for r in range(world)]
+    return [wl["frames"]] * world
 
 
 def run_reference(args, wl, name):
+    """`--impl reference`: the reference's own CPU implementation of the path on the box's host cores (rank 0 only)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     vals, base = [], None
-    # every step is a bounded sample (~13 s at full thickness on 16 threads); beyond 8 steps in all the samples get
-    # thinner so that the whole run stays within a few minutes
     total = args.warmup + args.steps
-    zf = 1.0 if total <= 8 else 8.0 / total
-    for i in range(total):
-        base = cpu_baseline(wl, zf)
-        if i >= args.warmup:
-            vals.append(base["value"])
-    v = float(np.mean(vals))
+    # every step is one bounded sample (~10-30 s); beyond 8 steps the sample shrinks to keep the run within minutes
+    n = reference_sample_frames(wl)
+    if total > 8:
+        n = max(2, n * 8 // total)
+    try:
+        for i in range(total):
+            v, base = reference_torch_step(wl, name, n_frames=n)
+            if i >= args.warmup:
+                vals.append(v)
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}))
+        return
+    v = float(np.median(vals))
     base["value"] = v
-    nz = wl["grid"][2]
+    base["all_steps"] = vals
+    P = wl["probes"] ** 2 if wl["probes"] else 1
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    cfg = config_block(wl, name, world, frame_counts(wl, world), int(make_traj(wl, 1).n_atoms), P)
+    base["note"] = "reference arm: one bounded sample of the workload in `config` per step (see sample), median of the steps"
     line = {"impl": "reference", "metric": "slice-steps/sec (probe*frame*slice)", "value": v, "unit": "slice-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * base["cores"] * base["slices"] / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "note": "CPU port of the reference path (oracle/), bounded frame sample per step"},
-            "cpu_baseline": base,
+            "ms_per_step": 1e3 * base["slice_steps_in_sample"] / v, "higher_is_better": True, "scaling": wl["scaling"],
+            "vs_baseline": None, "dtype": "c128 (torch CPU)", "data": "synthetic", "config": cfg, "cpu_baseline": base,
             "e2e": {"value": v, "unit": "slice-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+# ---- N-GPU == 1-GPU ------------------------------------------------------------------------------------------------
+def multi_gpu_parity(dev, rank, world):
+    """A small frame-sharded job over the real process group (NCCL on the GPU box) against the same job computed
+    unsharded by every rank: intensity rows bit for bit, reducers to float64 round-off (reference: the sequential frame
+    loop of src/multislice/calculators.py:172 + src/postprocessing/tacaw_data.py:89-104 -- the single-GPU result IS the
+    oracle of the sharded one).  256 x 256 x 9 slices, 8*world + 3 frames (ragged).  Returns "bitwise" or raises."""
+    import torch
+    import torch.distributed as dist
+    from pyslice_b200 import synthetic
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    from pyslice_b200.postprocessing.tacaw_data import TACAWData
+    T = 8 * world + 3
+    traj = synthetic.random_trajectory(n_atoms=400, box=(25.55, 25.55, 4.1), n_frames=T, seed=41, types=(6, 14))
+    calc = MultisliceCalculator(device=dev)
+    calc.setup(traj, aperture=0.0, voltage_eV=VOLTAGE)                          # sharded: world > 1
+    assert calc.shard is not None and sum(calc.shard.counts) == T
+    wf = calc.run()
+    tac = TACAWData(wf)
+    single = MultisliceCalculator(device=dev)
+    single.setup(traj, aperture=0.0, voltage_eV=VOLTAGE, shard_frames=False)
+    tac1 = TACAWData(single.run())
+    r0, r1 = tac.row_range
+    ok = bool(torch.equal(tac.intensity, tac1.intensity[:, :, r0:r1]))
+    s, s1 = tac.spectrum(), tac1.spectrum()                                     # collective inside: every rank calls
+    d, d1 = tac.diffraction(), tac1.diffraction()
+    ok = ok and bool(np.allclose(s, s1, rtol=1e-12, atol=0)) and bool(np.allclose(d, d1, rtol=1e-6, atol=0))
+    ok = ok and bool(np.abs(s1).max() > 0)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) != 1:
+        raise AssertionError(f"rank {rank}: sharded result differs from the single-GPU result")
+    return "bitwise"
 
 
 def main():
@@ -203,20 +391,22 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default=DEFAULT, choices=list(WORKLOADS))
-    ap.add_argument("--frames", type=int, default=0, help="override frames per GPU (debug)")
+    ap.add_argument("--workload", default=DEFAULT, choices=list(WORKLOADS) + list(ALIASES))
+    ap.add_argument("--frames", type=int, default=0, help="override the workload's frame count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (profiling runs)")
     args = ap.parse_args()
-    wl = dict(WORKLOADS[args.workload])
+    name = ALIASES.get(args.workload, args.workload)
+    wl = dict(WORKLOADS[name])
     if args.frames:
         wl["frames"] = args.frames
     if args.impl == "reference":
-        return run_reference(args, wl, args.workload)
+        return run_reference(args, wl, name)
 
     import torch
     import torch.distributed as dist
     from pyslice_b200 import engine
-    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    from pyslice_b200.multislice.calculators import FrameShard, MultisliceCalculator
     from pyslice_b200.multislice.trajectory import Trajectory
     from pyslice_b200.postprocessing.tacaw_data import TACAWData
 
@@ -229,12 +419,18 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    F = wl["frames"]
+    parity = multi_gpu_parity(dev, rank, world) if world > 1 else None
+
     nx, ny, nz = wl["grid"]
-    T_total = F * world
-    # every rank generates only its own block of the same global trajectory (weak scaling in frames)
-    local_traj = make_traj(wl, F, frame0=rank * F)
+    counts = frame_counts(wl, world)
+    F = counts[rank]
+    frame0 = sum(counts[:rank])
+    T_total = sum(counts)
+    # every rank generates only its own block of the same global trajectory
+    local_traj = make_traj(wl, F, frame0=frame0)
     A = local_traj.n_atoms
+    pp = probe_positions(wl, local_traj.box_matrix)
+    P = len(pp) if pp is not None else 1
 
     class ShardedCalc(MultisliceCalculator):
         """the public calculator, fed this rank's frame block directly (the global trajectory is never
@@ -244,10 +440,10 @@ def main():
 
     def setup_calc(traj):
         calc = ShardedCalc(device=dev)
-        calc.setup(traj, aperture=0.0, voltage_eV=VOLTAGE, shard_frames=False)
+        calc.setup(traj, aperture=wl["aperture"], voltage_eV=VOLTAGE, probe_positions=pp, layer_every=wl["layer_every"],
+                   shard_frames=False)
         if world > 1:
-            from pyslice_b200.multislice.calculators import FrameShard
-            calc.shard = FrameShard(rank, world, [F] * world)
+            calc.shard = FrameShard(rank, world, counts)
             calc.n_frames = T_total
         return calc
 
@@ -256,29 +452,44 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- arm 2 (timed first, see ClockSampler): end to end through the public API with host buffers ----
-    pinned = torch.empty(local_traj.positions.shape, dtype=torch.float64).pin_memory()
-    pinned.numpy()[...] = local_traj.positions
-    host_traj = Trajectory(local_traj.atom_types, pinned.numpy(), np.zeros((F, A, 3)), local_traj.box_matrix,
-                           local_traj.timestep)
     rows = nx // world + (1 if rank < nx % world else 0)
-    out_host = torch.empty((1, T_total, rows, ny), dtype=torch.float32).pin_memory()
 
-    def e2e_step():
-        c = setup_calc(host_traj)
-        wf = c.run()
-        tac = TACAWData(wf)
-        out_host.copy_(tac.intensity, non_blocking=True)
-        torch.cuda.synchronize()
+    def result_to_host(tac, out_host):
+        """the step's result leaves the device: the intensity cube of a plane-wave TACAW run (C1, C2, C4), the per-probe
+        spectra and the mean diffraction pattern of a STEM run (the cube is tens of GB there)"""
+        if P == 1:
+            out_host.copy_(tac.intensity, non_blocking=True)
+            torch.cuda.synchronize()
+            return out_host.numel() * 4
+        s = tac._sum_k()
+        d = tac.diffraction()
+        return s.nbytes + d.nbytes
 
-    for _ in range(args.warmup):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        e2e_step()
-    barrier()
-    ms_e2e = (time.perf_counter() - t0) * 1e3
+    # ---------------- arm 2 (timed first, see ClockSampler): end to end through the public API with host buffers ----
+    ms_e2e, d2h = None, 0
+    if not args.no_e2e:
+        pinned = torch.empty(local_traj.positions.shape, dtype=torch.float64).pin_memory()
+        pinned.numpy()[...] = local_traj.positions
+        host_traj = Trajectory(local_traj.atom_types, pinned.numpy(), np.zeros((F, A, 3)),
+                               local_traj.box_matrix, local_traj.timestep)
+        out_host = torch.empty((1, T_total, rows, ny), dtype=torch.float32).pin_memory() if P == 1 else None
+
+        def e2e_step():
+            c = setup_calc(host_traj)
+            wf = c.run()
+            tac = TACAWData(wf)
+            return result_to_host(tac, out_host)
+
+        for _ in range(args.warmup):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            d2h = e2e_step()
+        barrier()
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        del pinned, host_traj, out_host
+        torch.cuda.empty_cache()
 
     # ---------------- arm 1: inputs resident in HBM ------------------------------------------
     pos_dev = torch.from_numpy(local_traj.positions).to(dev)
@@ -286,11 +497,12 @@ def main():
     dev_traj.atom_types, dev_traj.positions, dev_traj.velocities = local_traj.atom_types, pos_dev, None
     dev_traj.box_matrix, dev_traj.timestep = local_traj.box_matrix, local_traj.timestep
     calc = setup_calc(dev_traj)
-    assert (calc.nx, calc.ny, calc.nz) == (nx, ny, nz)
+    assert (calc.nx, calc.ny, calc.nz) == (nx, ny, nz), (calc.nx, calc.ny, calc.nz)
     timer = engine.PhaseTimer(dev)
 
     def device_step(tm=None):
         wf = calc.run(timer=tm)
+        wf._timer = tm
         tac = TACAWData(wf)
         return tac
 
@@ -301,13 +513,16 @@ def main():
         sampler.start()
         sampler.wait_ready()
     for _ in range(args.warmup):
-        device_step()
+        tac = device_step()
+        del tac
     barrier()
     sampler.mark()
     l0 = engine.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    tac = None
     for _ in range(args.steps):
+        del tac
         tac = device_step(timer)
     e1.record()
     barrier()
@@ -316,62 +531,82 @@ def main():
     phases = timer.totals()
     clocks = sampler.stop() if rank == 0 else None
     spectrum = tac.spectrum()          # touches the result (and checks the reducers run)
-    assert np.isfinite(spectrum).all()
+    assert np.isfinite(spectrum).all() and np.abs(spectrum).max() > 0
     del tac
 
+    keys = ["propagate", "potential", "all_to_all", "tacaw"]
+    vals = [ms_dev, ms_e2e or 0.0] + [phases.get(k, 0.0) for k in keys]
     if world > 1:
-        t = torch.tensor([ms_dev, ms_e2e, phases.get("propagate", 0.0), phases.get("potential", 0.0)],
-                         dtype=torch.float64, device=dev)
+        t = torch.tensor(vals, dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_dev, ms_e2e, prop_ms, pot_ms = t.tolist()
-    else:
-        prop_ms, pot_ms = phases.get("propagate", 0.0), phases.get("potential", 0.0)
+        vals = t.tolist()
+    ms_dev, ms_e2e_max = vals[0], vals[1]
+    prop_ms, pot_ms, a2a_ms, tacaw_ms = vals[2:6]
 
     if rank == 0:
-        slice_steps = 1 * T_total * nz                       # probes * frames * slices, whole job
+        slice_steps = P * T_total * nz                       # probes * frames * slices, whole job
         value = slice_steps * args.steps / (ms_dev * 1e-3)
-        e2e_value = slice_steps * args.steps / (ms_e2e * 1e-3)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        b_ss = nx * ny * (16 + 4 / 1)                        # psi r+w (c64) + fp32 phase, B = 1 probe
-        per_gpu_steps = F * nz * args.steps
+        b_ss = nx * ny * (16 + 4 / P)                        # psi r+w (c64) + fp32 phase shared by P probes
+        per_gpu_steps = P * max(counts) * nz * args.steps
         achieved = per_gpu_steps * b_ss / (prop_ms * 1e-3) / 1e9 if prop_ms > 0 else None
-        traffic = None
+        traffic_doc = {}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("slice_step_dram_bytes_per_launch")
+            traffic_doc = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         except Exception:
             pass
+        traffic = traffic_doc.get("by_grid", {}).get(f"{nx}x{ny}", {}).get("dram_bytes_per_launch_pair",
+                                                                          traffic_doc.get("slice_step_dram_bytes_per_launch") if nx == 256 else None)
+        fb = engine.batch_sizes(calc._plan, P, max(F, 1))[0]
+        cfg = config_block(wl, name, world, counts, A, P)
+        lanes = FP32_LANE_CYCLES_PER_PIXEL.get(max(nx, ny))
+        sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+        fp32_floor = None
+        if lanes:
+            floor_steps = 148 * 128 * sm_clock * 1e6 / (lanes * nx * ny)        # slice-steps/s with the fp32 pipe 100 % busy
+            fp32_floor = {"lane_cycles_per_pixel": lanes, "slice_steps_per_s_at_full_pipe": floor_steps,
+                          "frac_of_floor": (per_gpu_steps / (prop_ms * 1e-3)) / floor_steps if prop_ms > 0 else None,
+                          "hbm_roofline_slice_steps_per_s": peak * 1e9 / b_ss,
+                          "note": "the transforms' own packed-fp32 instruction count bounds the slice step at this rate "
+                                  "(DESIGN.md 4.1); where it is below the HBM roofline, frac cannot reach 1"}
         line = {
             "metric": "slice-steps/sec (probe*frame*slice)", "value": value, "unit": "slice-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c64 (fp32 complex)",
-            "data": "synthetic",
-            "config": {"workload": args.workload, "grid": [nx, ny, nz], "atoms": A, "frames_per_gpu": F,
-                       "frames_total": T_total, "probes": 1, "voltage_eV": VOLTAGE,
-                       "l2": "inputs larger than L2: every timed step streams the positions and a >= 30 GB transmission stack per "
-                             "frame batch through HBM; only the psi batch (<= 80 MB) is L2-resident by design; no explicit flush",
-                       "frames_per_batch": engine.batch_sizes(calc._plan, 1, F)[0],
-                       "tacaw_wall_ms": ms_dev / args.steps, "parallelism": f"frames sharded over {world} GPU(s), all-to-all to kx rows"},
-            "e2e": {"value": e2e_value, "unit": "slice-steps/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": int(F * A * 3 * 8), "d2h_bytes_per_step": int(T_total * rows * ny * 4),
-                    "api": "MultisliceCalculator.setup()/run() + TACAWData(wf), pinned host positions in, intensity out"},
+            "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "c64 (fp32 complex)",
+            "data": "synthetic", "config": cfg,
+            "run": {"frames_per_batch": fb, "tacaw_wall_ms": ms_dev / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "phases_ms_per_step": {"potential": pot_ms / args.steps, "propagate_incl_exit_fft": prop_ms / args.steps,
-                                   "other_incl_tacaw": (ms_dev - pot_ms - prop_ms) / args.steps},
-            "roofline": {"bound": "hbm", "kernel": "slice-step = fast_rows_kernel<256,3> + fast_cols_kernel<256,256,0> (psb_propagate_phase)",
+                                   "all_to_all": a2a_ms / args.steps, "tacaw": tacaw_ms / args.steps,
+                                   "other": (ms_dev - pot_ms - prop_ms - a2a_ms - tacaw_ms) / args.steps},
+            "roofline": {"bound": "hbm", "kernel": f"slice-step = fused row pass + column pass at {nx} x {ny} "
+                                                   f"({'float32 phase stack' if P == 1 else 'complex64 transmission stack'})",
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if achieved else None, "traffic": traffic,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes_per_slice_step": b_ss,
-                         "traffic_note": "ncu dram bytes per launch pair (row + column pass, cold L2 under ncu), see profiles/roofline_traffic.json"},
+                         "algorithmic_bytes_per_slice_step": b_ss, "fp32_floor": fp32_floor,
+                         "traffic_note": "ncu dram bytes per launch pair (row + column pass), see profiles/roofline_traffic.json"},
         }
+        if ms_e2e is not None:
+            line["e2e"] = {"value": slice_steps * args.steps / (ms_e2e_max * 1e-3), "unit": "slice-steps/s",
+                           "ms_per_step": ms_e2e_max / args.steps,
+                           "h2d_bytes_per_step": int(F * A * 3 * 8), "d2h_bytes_per_step": int(d2h),
+                           "api": "MultisliceCalculator.setup()/run() + TACAWData(wf), pinned host positions in, " +
+                                  ("intensity cube out" if P == 1 else "per-probe spectra + diffraction pattern out")}
+        if a2a_ms > 0 and world > 1:
+            sent = 8.0 * P * F * nx * ny * (world - 1) / world * args.steps         # bytes this rank sends per run
+            line["all_to_all"] = {"ms_per_step": a2a_ms / args.steps, "bytes_sent_per_rank_per_step": sent / args.steps,
+                                  "gb_per_s_per_rank": sent / (a2a_ms * 1e-3) / 1e9, "backend": "nccl all_to_all_single"}
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(wl)
+            line["cpu_baseline"] = cpu_baseline(wl, name)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

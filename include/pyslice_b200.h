@@ -43,8 +43,7 @@ void psb_release_tables(void);
 /* kernels launched by this library in this process so far (benchmark bookkeeping) */
 long long psb_launch_count(void);
 /* diagnostic switch between kernel generations (all CUDA; used by microbenchmarks and A/B parity tests):
- * 0 = generic line-pass kernels, 1 = fused persistent kernels (default), 2 = 1 plus the experimental
- * structure-factor + column-transform fusion (csrc/sf_cols.cu, measured slower on B200). */
+ * 0 = generic line-pass kernels, anything else = fused persistent kernels (default). */
 void psb_set_fast_path(int level);
 
 /* ---- atom -> slice binning: src/multislice/potentials.py:297-317 (+ bounds :304-305) -------------

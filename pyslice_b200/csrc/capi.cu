@@ -63,7 +63,6 @@ void psb_release_tables(void) {
     free_all_tables();
 #ifndef PSB_EMU
     sf_fast_release();
-    sf_cols_release();
     tacaw_fast_release();
 #endif
 }
@@ -149,7 +148,9 @@ static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t
     const int TXs = StructureFactorPaired::TX, TYs = StructureFactorPaired::TY;
     const int tiles = ((StructureFactorPaired::slots(nx) + TXs - 1) / TXs) * ((StructureFactorPaired::slots(ny) + TYs - 1) / TYs);
 #ifndef PSB_EMU
-    if (fast_path_enabled()) {
+    // pipelined structure factor (sf_fast.cu) unless the type count exceeds what it stages: then the generic kernel
+    const bool sf_fast = fast_path_enabled() && sf_fast_supported(ntypes);
+    if (sf_fast) {
         int rc0 = sf_fast_prepare(formfactors, ntypes, nx, ny, s);
         if (rc0 != PSB_OK) return rc0;
     }
@@ -184,16 +185,7 @@ static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t
             groups = (nm + sp.pairs_per_block - 1) / sp.pairs_per_block;
             int rc;
 #ifndef PSB_EMU
-            if (fast_path_enabled() && sf_cols_supported(nx, ny, nf * nm)) {
-                // structure factor + inverse column transform in one persistent kernel (sf_cols.cu), then the
-                // inverse row transform with the transmission epilogue
-                rc = launch_sf_cols(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, sf_fast_ff4(), f2(scratch), s);
-                if (rc != PSB_OK) return rc;
-                rc = rows_out(nf, nm, f0, mb);
-                if (rc != PSB_OK) return rc;
-                continue;
-            }
-            if (fast_path_enabled())
+            if (sf_fast)
                 rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, f2(scratch), s);
             else
 #endif

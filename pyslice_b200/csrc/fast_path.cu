@@ -155,17 +155,24 @@ constexpr bool row_mode_steps(int mode) { return mode == R_STEP || mode == R_STE
 #define PSB_ROW_TBUFS 1
 #endif
 
+// warps per CTA of the phase-format slice step (R_STEP_PHASE): its transmission landing buffer is half the size, which
+// leaves room for 20 warps (5 per scheduler) in shared memory and, at <= 96 registers, in the register file
+#ifndef PSB_ROW_WARPS_PHASE
+#define PSB_ROW_WARPS_PHASE 16
+#endif
+
 template <int N, int MODE = 0>
 struct RowCfg {
     static constexpr int T = N / 16;               // threads per line
     static constexpr int LPW = 32 / T;             // lines per warp
     static constexpr int NP = N + N / 16;          // padded exchange pitch
     static constexpr int kTBufs = (MODE == 0) ? PSB_ROW_TBUFS : 1;
-    static constexpr int kWarps = (kTBufs == 1) ? 16 : 12;
+    static constexpr int kWarps = (MODE == 3) ? PSB_ROW_WARPS_PHASE : ((kTBufs == 1) ? 16 : 12);
     static constexpr int kThreads = 32 * kWarps;
     static constexpr int kLand = LPW * N;          // float2 per landing buffer (4 KB)
+    static constexpr int kTLand = (MODE == 3) ? kLand / 2 : kLand;     // transmission rows of a unit: float phases or complex t
     static constexpr int kX = LPW * NP;
-    static constexpr int kWarpElems = (1 + kTBufs) * kLand + kX;
+    static constexpr int kWarpElems = kLand + kTBufs * kTLand + kX;
     static constexpr int kBars = 1 + kTBufs;
     static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + kWarps * kBars * sizeof(uint64_t);
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
@@ -191,7 +198,7 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
     const int lane = threadIdx.x & 31;
     cpx* land_psi = sm + (size_t)warp * C::kWarpElems;
     cpx* land_t = land_psi + C::kLand;                       // [kTBufs][kLand]
-    cpx* xb = land_t + C::kTBufs * C::kLand;
+    cpx* xb = land_t + C::kTBufs * C::kTLand;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)C::kWarps * C::kWarpElems) + C::kBars * warp;
     uint64_t* mb_psi = bars;
     uint64_t* mb_t = bars + 1;                               // [kTBufs]
@@ -235,7 +242,7 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
         }
         if (row_mode_steps(MODE) && want_t) {
             mbar_expect_tx(mb_t + tb, C::kTBytes);
-            bulk_g2s_hint(land_t + tb * C::kLand, t_rows(unit), C::kTBytes, mb_t + tb, stream_once);
+            bulk_g2s_hint(land_t + tb * C::kTLand, t_rows(unit), C::kTBytes, mb_t + tb, stream_once);
         }
     };
     if (u < n_units && lane == 0) {
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
         // exchange: its stores depend on every value loaded from them, so those loads have completed by then.
         // (Issuing right after a __syncwarp let the next unit's TMA overwrite words whose LDS was still in flight.)
         const cpx* lp = land_psi + c * N + j;
-        const cpx* lt = land_t + tb * C::kLand + c * N + j;
+        const cpx* lt = land_t + tb * C::kTLand + c * N + j;
         if constexpr (row_mode_steps(MODE)) {
             cpx v[16];
             const float* ltf = reinterpret_cast<const float*>(land_t) + c * N + j;      // R_STEP_PHASE: float rows
@@ -496,12 +503,9 @@ int encode_cols_map(CUtensorMap* map, float2* psi, long long rows_total, int ny,
 template <int N, int MODE>
 int rows_go(const RowPassParams& p, cudaStream_t s) {
     using C = RowCfg<N, MODE>;
-    static bool ready = false;
-    if (!ready) {
-        int rc = ensure_smem(fast_rows_kernel<N, MODE>, C::kSmem, "fast row pass");
-        if (rc != PSB_OK) return rc;
-        ready = true;
-    }
+    static rt::PerDeviceOnce once;
+    int rc0 = once.run([] { return ensure_smem(fast_rows_kernel<N, MODE>, C::kSmem, "fast row pass"); });
+    if (rc0 != PSB_OK) return rc0;
     long long want = (p.n_units + C::kWarps - 1) / C::kWarps;
     const int sms = rt::sm_count();
     const int grid = (int)(want < sms ? want : sms);
@@ -514,16 +518,15 @@ int rows_go(const RowPassParams& p, cudaStream_t s) {
 template <int N, int NY, int MODE>
 int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const float2* tw, cudaStream_t s) {
     using C = ColCfg<N>;
-    static bool ready = false;
-    if (!ready) {
-        int rc = ensure_smem(fast_cols_kernel<N, NY, MODE>, C::kSmem + NY * sizeof(float2), "fast column pass");
-        if (rc != PSB_OK) return rc;
-        ready = true;
-    }
-    // the tensor map depends on the buffer and the batch size only: keep the last one
-    static CUtensorMap map;
-    static float2* map_psi = nullptr;
-    static int map_img = -1;
+    static rt::PerDeviceOnce once;
+    int rc0 = once.run([] { return ensure_smem(fast_cols_kernel<N, NY, MODE>, C::kSmem + NY * sizeof(float2), "fast column pass"); });
+    if (rc0 != PSB_OK) return rc0;
+    // the tensor map depends on the buffer and the batch size only: keep the last one of this host thread (a map is
+    // plain host data passed by value at launch, so a per-thread cache needs no lock and cannot cross devices: device
+    // pointers of different GPUs never compare equal under unified addressing)
+    static thread_local CUtensorMap map;
+    static thread_local float2* map_psi = nullptr;
+    static thread_local int map_img = -1;
     if (map_psi != psi || map_img != n_img) {
         int rc = encode_cols_map(&map, psi, (long long)n_img * N, NY, C::W, C::kBoxRows);
         if (rc != PSB_OK) return rc;
@@ -543,7 +546,7 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const fl
 
 }  // namespace
 
-void fast_path_enable(int level) { g_fast_enabled.store(level < 0 ? 0 : (level > 2 ? 2 : level)); }
+void fast_path_enable(int level) { g_fast_enabled.store(level <= 0 ? 0 : 1); }
 bool fast_path_enabled() { return g_fast_enabled.load() != 0; }
 int fast_path_level() { return g_fast_enabled.load(); }
 

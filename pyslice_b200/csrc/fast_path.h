@@ -6,9 +6,8 @@ namespace psb {
 
 // true when both passes of a slice step have a fused kernel for this grid (and the fast path is enabled)
 bool fast_slice_supported(int nx, int ny);
-// level 0: generic line passes only; 1 (default): fused slice-step / transmission kernels, pipelined structure
-// factor (sf_fast.cu) and stand-alone column pass; 2: experimental -- structure factor fused with the inverse
-// column transform (sf_cols.cu; measured slower than level 1 on B200, kept for the A/B tests)
+// level 0: generic line passes only; 1 (default): fused slice-step / transmission kernels and pipelined structure
+// factor (sf_fast.cu)
 void fast_path_enable(int level);
 bool fast_path_enabled();
 int fast_path_level();
@@ -40,15 +39,6 @@ int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s)
 int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
                    int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s);
 void sf_fast_release();
-#ifndef PSB_EMU
-const float4* sf_fast_ff4();      // the table gathered by the last sf_fast_prepare
-
-// structure factor + inverse column transform of slice pairs [pair_begin, pair_begin + pair_count) of nf frames
-// (sf_cols.cu): out (nf * pair_count, nx, ny) holds IFFT_x of the paired spectra, ready for launch_fast_rows_transmit
-bool sf_cols_supported(int nx, int ny, int n_img);
-int launch_sf_cols(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
-                   int ny, int pair_begin, int pair_count, int nf, const float4* ff4, float2* out, cudaStream_t s);
-void sf_cols_release();
-#endif
+bool sf_fast_supported(int ntypes);      // the pipelined kernel stages at most 64 atom types; beyond that the generic kernel runs
 
 }  // namespace psb

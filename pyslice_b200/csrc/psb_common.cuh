@@ -38,6 +38,7 @@ static inline void sincospif(float x, float* s, float* c) {
 template <class T> static inline T __ldg(const T* p) { return *p; }
 static inline float __int2float_rn(int v) { return (float)v; }
 #else
+#include <atomic>
 #include <cuda_runtime.h>
 #define PSB_HD __host__ __device__ __forceinline__
 #define PSB_D __device__ __forceinline__
@@ -47,8 +48,8 @@ static inline float __int2float_rn(int v) { return (float)v; }
 namespace psb {
 
 // number of kernel launches issued by this library (bench.py reports it as gpu_launches)
-inline long long& launch_counter() {
-    static long long n = 0;
+inline std::atomic<long long>& launch_counter() {
+    static std::atomic<long long> n{0};
     return n;
 }
 
@@ -92,11 +93,15 @@ __global__ void __launch_bounds__(K::kThreads, K::kMinBlocks) psb_kernel(const P
 template <class K, class P>
 inline cudaError_t launch(dim3 grid, size_t smem, cudaStream_t stream, const P& p) {
     if (smem > 48 * 1024) {
-        static size_t granted = 0;   // per instantiation
-        if (smem > granted) {
+        // the opt-in is a per-device function attribute: remember what was granted per device ordinal
+        static std::atomic<size_t> granted[64];   // per instantiation, zero-initialised
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (smem > granted[d].load(std::memory_order_acquire)) {
             cudaError_t e = cudaFuncSetAttribute(psb_kernel<K, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            granted = smem;
+            granted[d].store(smem, std::memory_order_release);
         }
     }
     psb_kernel<K, P><<<grid, K::kThreads, smem, stream>>>(p);

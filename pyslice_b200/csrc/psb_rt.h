@@ -4,6 +4,8 @@
 #include "psb_common.cuh"
 #include "../../include/pyslice_b200.h"   // psb_status codes
 
+#include <atomic>
+#include <mutex>
 #include <string>
 
 namespace psb {
@@ -20,6 +22,24 @@ int zero(void* dst, size_t bytes, cudaStream_t s);
 int device();                                  // current device ordinal
 int check(const char* what);                   // cudaGetLastError -> psb code
 int sm_count();
+
+// One-time set-up that CUDA keeps per device (cudaFuncSetAttribute, ...): `run(f)` calls f() the first time the object is
+// used on the CURRENT device and remembers success per device ordinal, under a lock, so a process that drives several
+// GPUs (or several host threads) never skips the set-up on a device that has not seen it.
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> done{0};
+    std::mutex mu;
+    template <class F>
+    int run(F&& f) {
+        const int d = device() & 63;
+        if ((done.load(std::memory_order_acquire) >> d) & 1ull) return PSB_OK;
+        std::lock_guard<std::mutex> lk(mu);
+        if ((done.load(std::memory_order_relaxed) >> d) & 1ull) return PSB_OK;
+        const int rc = f();
+        if (rc == PSB_OK) done.fetch_or(1ull << d, std::memory_order_release);
+        return rc;
+    }
+};
 }  // namespace rt
 
 }  // namespace psb

@@ -22,6 +22,7 @@
 #include "psb_rt.h"
 
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 
@@ -374,46 +375,63 @@ __global__ void __launch_bounds__(256, 2) sf_tiles_kernel(const SfFastParams p) 
         }
 }
 
-// grow-only workspace for the phase tables, one per process (one process per GPU)
+// grow-only workspaces (phase tables, gathered form factors), one set per (device, stream): calls on different GPUs or
+// on different streams of one GPU never share a block
+struct SfWorkspace {
+    void* ws = nullptr;
+    size_t ws_bytes = 0;
+    void* ff4 = nullptr;       // gathered form factors of the current psb_build_transmission call
+    size_t ff4_bytes = 0;
+};
 std::mutex g_ws_mu;
-void* g_ws = nullptr;
-size_t g_ws_bytes = 0;
-void* g_ff4 = nullptr;         // gathered form factors of the current psb_build_transmission call
-size_t g_ff4_bytes = 0;
+std::map<std::pair<int, cudaStream_t>, SfWorkspace> g_ws;
+SfWorkspace& workspace_of(cudaStream_t s) { return g_ws[std::make_pair(rt::device(), s)]; }    // g_ws_mu held
 
 }  // namespace
 
 void sf_fast_release() {
     std::lock_guard<std::mutex> lk(g_ws_mu);
-    rt::dev_free(g_ws);
-    rt::dev_free(g_ff4);
-    g_ws = g_ff4 = nullptr;
-    g_ws_bytes = g_ff4_bytes = 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : g_ws) {
+        cudaSetDevice(kv.first.first);
+        rt::dev_free(kv.second.ws);
+        rt::dev_free(kv.second.ff4);
+    }
+    cudaSetDevice(cur);
+    g_ws.clear();
 }
 
-const float4* sf_fast_ff4() {
+const float4* sf_fast_ff4(cudaStream_t s) {
     std::lock_guard<std::mutex> lk(g_ws_mu);
-    return reinterpret_cast<const float4*>(g_ff4);
+    return reinterpret_cast<const float4*>(workspace_of(s).ff4);
 }
 
 int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s) {
     const size_t n = (size_t)ntypes * StructureFactorPaired::slots(nx) * StructureFactorPaired::slots(ny);
-    std::lock_guard<std::mutex> lk(g_ws_mu);
-    if (n * sizeof(float4) > g_ff4_bytes) {
-        cudaError_t e = cudaStreamSynchronize(s);
-        if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf workspace sync: ") + cudaGetErrorString(e));
-        rt::dev_free(g_ff4);
-        g_ff4 = rt::dev_alloc(n * sizeof(float4));
-        g_ff4_bytes = g_ff4 ? n * sizeof(float4) : 0;
-        if (!g_ff4) return PSB_ERR_NOMEM;
+    float4* ff4 = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        SfWorkspace& w = workspace_of(s);
+        if (n * sizeof(float4) > w.ff4_bytes) {
+            cudaError_t e = cudaStreamSynchronize(s);
+            if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf workspace sync: ") + cudaGetErrorString(e));
+            rt::dev_free(w.ff4);
+            w.ff4 = rt::dev_alloc(n * sizeof(float4));
+            w.ff4_bytes = w.ff4 ? n * sizeof(float4) : 0;
+            if (!w.ff4) return PSB_ERR_NOMEM;
+        }
+        ff4 = reinterpret_cast<float4*>(w.ff4);
     }
     const long long blocks = (long long)((n + 255) / 256);
-    ff4_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, s>>>(ff, reinterpret_cast<float4*>(g_ff4), ntypes, nx, ny);
+    ff4_kernel<<<(unsigned)(blocks < 1184 ? blocks : 1184), 256, 0, s>>>(ff, ff4, ntypes, nx, ny);
     ++launch_counter();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("ff4 launch: ") + cudaGetErrorString(e));
     return PSB_OK;
 }
+
+bool sf_fast_supported(int ntypes) { return ntypes <= kMaxStagedTypes; }
 
 int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
                    int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s) {
@@ -429,27 +447,29 @@ int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned in
     const size_t need = (nx_elems + ny_elems) * sizeof(float2) + 2 * sn_elems * sizeof(float) + 256;
     {
         std::lock_guard<std::mutex> lk(g_ws_mu);
-        if (need > g_ws_bytes) {
+        SfWorkspace& w = workspace_of(s);
+        if (need > w.ws_bytes) {
             cudaError_t e = cudaStreamSynchronize(s);      // kernels of earlier chunks may still read the old block
             if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf workspace sync: ") + cudaGetErrorString(e));
-            rt::dev_free(g_ws);
-            g_ws = rt::dev_alloc(need);
-            g_ws_bytes = g_ws ? need : 0;
-            if (!g_ws) return PSB_ERR_NOMEM;
+            rt::dev_free(w.ws);
+            w.ws = rt::dev_alloc(need);
+            w.ws_bytes = w.ws ? need : 0;
+            if (!w.ws) return PSB_ERR_NOMEM;
         }
-        if (!g_ff4) return fail(PSB_ERR_INVALID, "launch_sf_fast without sf_fast_prepare");
-        p.ff4 = reinterpret_cast<const float4*>(g_ff4);
-        p.tabx = reinterpret_cast<float2*>(g_ws);
+        if (!w.ff4) return fail(PSB_ERR_INVALID, "launch_sf_fast without sf_fast_prepare");
+        p.ff4 = reinterpret_cast<const float4*>(w.ff4);
+        p.tabx = reinterpret_cast<float2*>(w.ws);
         p.taby = p.tabx + nx_elems;
         p.snx = reinterpret_cast<float*>(p.taby + ny_elems);
         p.sny = p.snx + sn_elems;
     }
-    static bool ready = false;
-    if (!ready) {
+    static rt::PerDeviceOnce once;
+    int rc0 = once.run([] {
         cudaError_t e = cudaFuncSetAttribute(sf_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSfSmem);
         if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf tiles: ") + cudaGetErrorString(e));
-        ready = true;
-    }
+        return (int)PSB_OK;
+    });
+    if (rc0 != PSB_OK) return rc0;
     if (cap > 0) {
         cudaError_t e1 = pdl_launch(phase_tables_kernel, dim3((cap + 7) / 8, nf), dim3(256), 0, s, p);
         ++launch_counter();

@@ -119,11 +119,12 @@ int get_tables(int T, TwTables* out, cudaStream_t s) {
 template <int PX, int kThreads>
 int go(const TwFastParams& p, int n_probes, cudaStream_t s) {
     const size_t smem = (size_t)p.T * PX * sizeof(float2);
-    static size_t smem_set = 0;
-    if (smem > smem_set) {
+    static std::atomic<size_t> smem_set[64];          // per device ordinal (the attribute is per device), zero-initialised
+    const int d = rt::device() & 63;
+    if (smem > smem_set[d].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(tacaw_fast_kernel<PX, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("tacaw fast path: ") + cudaGetErrorString(e));
-        smem_set = smem;
+        smem_set[d].store(smem, std::memory_order_release);
     }
     const long long tiles = (p.npix + PX - 1) / PX;
     tacaw_fast_kernel<PX, kThreads><<<dim3((unsigned)tiles, (unsigned)n_probes), kThreads, smem, s>>>(p);

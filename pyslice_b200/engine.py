@@ -81,8 +81,7 @@ def launch_count() -> int:
 
 def set_fast_path(enable) -> None:
     """Diagnostic switch between the kernel generations (all CUDA; used by A/B parity tests and microbenchmarks):
-    True / 1 = fused persistent kernels (default), 2 = experimental: structure factor fused with the inverse column
-    transform (sf_cols.cu), False / 0 = generic line-pass kernels."""
+    True / 1 = fused persistent kernels (default), False / 0 = generic line-pass kernels."""
     level = 1 if enable is True else (0 if enable is False else int(enable))
     _lib.lib().psb_set_fast_path(level)
 
@@ -106,6 +105,30 @@ def _stream(device: torch.device) -> int:
     if device.type != "cuda":
         return 0
     return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on:
+    """`with _on(device):` makes `device` the current CUDA device around a libpsb call.  The library launches on the
+    CURRENT device and keys its tables and workspaces by it, while every buffer it is handed lives on the tensor's
+    device: with several GPUs in one process (MultisliceCalculator(device='cuda:1') while cuda:0 is current) the two
+    must be made to agree here.  No-op on the kernel emulator (tests) and when the device is already current."""
+
+    def __init__(self, device):
+        self.guard = None
+        if device is not None and getattr(device, "type", None) == "cuda" and not _lib.is_emulated():
+            idx = device.index if device.index is not None else torch.cuda.current_device()
+            if idx != torch.cuda.current_device():
+                self.guard = torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            return self.guard.__exit__(*exc)
+        return False
 
 
 def _c64(x: np.ndarray, device) -> torch.Tensor:
@@ -177,7 +200,8 @@ def fft2(x: torch.Tensor, inverse: bool = False, scale: float = 1.0, out: Option
     if out is None:
         out = torch.empty_like(x)
     L = _lib.lib()
-    _lib.check(L.psb_fft2(x.data_ptr(), out.data_ptr(), batch, nx, ny, 1 if inverse else 0, scale, _stream(x.device)), "psb_fft2")
+    with _on(x.device):
+        _lib.check(L.psb_fft2(x.data_ptr(), out.data_ptr(), batch, nx, ny, 1 if inverse else 0, scale, _stream(x.device)), "psb_fft2")
     return out
 
 
@@ -192,10 +216,11 @@ def bin_atoms(plan: SlicePlan, positions: torch.Tensor):
     ux = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
     uy = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
     L = _lib.lib()
-    _lib.check(L.psb_bin_atoms(positions.data_ptr(), plan.type_idx.data_ptr(), F, A, plan.ntypes, plan.nz,
-                               plan.lo.data_ptr(), plan.hi.data_ptr(), plan.dz, plan.nx * plan.dx, plan.ny * plan.dy,
-                               seg.data_ptr(), offsets.data_ptr(), atom_list.data_ptr(), ux.data_ptr(), uy.data_ptr(),
-                               _stream(dev)), "psb_bin_atoms")
+    with _on(dev):
+        _lib.check(L.psb_bin_atoms(positions.data_ptr(), plan.type_idx.data_ptr(), F, A, plan.ntypes, plan.nz,
+                                   plan.lo.data_ptr(), plan.hi.data_ptr(), plan.dz, plan.nx * plan.dx, plan.ny * plan.dy,
+                                   seg.data_ptr(), offsets.data_ptr(), atom_list.data_ptr(), ux.data_ptr(), uy.data_ptr(),
+                                   _stream(dev)), "psb_bin_atoms")
     return offsets, atom_list, ux, uy
 
 
@@ -241,25 +266,28 @@ def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential:
         assert not want_potential
         ph = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev)
         assert ph.dtype == torch.float32
-        _lib.check(L.psb_build_phase(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
-                                     plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
-                                     ph.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(dev)), "psb_build_phase")
+        with _on(dev):
+            _lib.check(L.psb_build_phase(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
+                                         plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
+                                         ph.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(dev)), "psb_build_phase")
         return ph
     t = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device=dev)
     V = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev) if want_potential else None
-    _lib.check(L.psb_build_transmission(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
-                                        plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
-                                        t.data_ptr(), V.data_ptr() if V is not None else None, scratch.data_ptr(),
-                                        scratch.numel(), _stream(dev)),
-               "psb_build_transmission")
+    with _on(dev):
+        _lib.check(L.psb_build_transmission(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
+                                            plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
+                                            t.data_ptr(), V.data_ptr() if V is not None else None, scratch.data_ptr(),
+                                            scratch.numel(), _stream(dev)),
+                   "psb_build_transmission")
     return (t, V) if want_potential else t
 
 
 def transmission_from_potential(V: torch.Tensor, sigma: float) -> torch.Tensor:
     assert V.dtype == torch.float32 and V.is_contiguous()
     t = torch.empty(V.shape, dtype=torch.complex64, device=V.device)
-    _lib.check(_lib.lib().psb_transmission_from_potential(V.data_ptr(), t.data_ptr(), V.numel(), sigma, _stream(V.device)),
-               "psb_transmission_from_potential")
+    with _on(V.device):
+        _lib.check(_lib.lib().psb_transmission_from_potential(V.data_ptr(), t.data_ptr(), V.numel(), sigma, _stream(V.device)),
+                   "psb_transmission_from_potential")
     return t
 
 
@@ -268,8 +296,9 @@ def shift_probes(base_k: torch.Tensor, ramp_x: torch.Tensor, ramp_y: torch.Tenso
     P = ramp_x.shape[0]
     nx, ny = base_k.shape
     out = torch.empty((P, nx, ny), dtype=torch.complex64, device=base_k.device)
-    _lib.check(_lib.lib().psb_shift_probes(base_k.data_ptr(), ramp_x.data_ptr(), ramp_y.data_ptr(), P, nx, ny,
-                                           out.data_ptr(), _stream(base_k.device)), "psb_shift_probes")
+    with _on(base_k.device):
+        _lib.check(_lib.lib().psb_shift_probes(base_k.data_ptr(), ramp_x.data_ptr(), ramp_y.data_ptr(), P, nx, ny,
+                                               out.data_ptr(), _stream(base_k.device)), "psb_shift_probes")
     return out
 
 
@@ -305,13 +334,15 @@ def propagate(plan: SlicePlan, probes: torch.Tensor, t: torch.Tensor, wf_out: Op
             return L.psb_propagate(probes.data_ptr(), t.data_ptr(), F, P, nz, nx, ny, plan.prop_x.data_ptr(),
                                    plan.prop_y.data_ptr(), work.data_ptr(), mode, base, sp, sf, sl, le, st)
     if wf_out is None:
-        _lib.check(call(0, None, 0, 0, 0, 0), "psb_propagate")
+        with _on(plan.device):
+            _lib.check(call(0, None, 0, 0, 0, 0), "psb_propagate")
         return work.view(F, P, nx, ny)
     Lr, Pt, Tt = wf_out.shape[:3]
     assert wf_out.is_contiguous() and Lr == layer_count(nz, layer_every)
     img = nx * ny
     base = wf_out.data_ptr() + 8 * (probe0 * Tt * img + frame0 * img)
-    _lib.check(call(1, base, Tt * img, img, Pt * Tt * img, layer_every), "psb_propagate")
+    with _on(plan.device):
+        _lib.check(call(1, base, Tt * img, img, Pt * Tt * img, layer_every), "psb_propagate")
     return wf_out
 
 
@@ -320,8 +351,9 @@ def tacaw_intensity(wf_layer: torch.Tensor) -> torch.Tensor:
     P, T, nx, ny = wf_layer.shape
     assert wf_layer.dtype == torch.complex64 and wf_layer.stride(3) == 1 and wf_layer.stride(2) == ny
     out = torch.empty((P, T, nx, ny), dtype=torch.float32, device=wf_layer.device)
-    _lib.check(_lib.lib().psb_tacaw_intensity(wf_layer.data_ptr(), wf_layer.stride(0), wf_layer.stride(1), P, T,
-                                              nx * ny, out.data_ptr(), _stream(wf_layer.device)), "psb_tacaw_intensity")
+    with _on(wf_layer.device):
+        _lib.check(_lib.lib().psb_tacaw_intensity(wf_layer.data_ptr(), wf_layer.stride(0), wf_layer.stride(1), P, T,
+                                                  nx * ny, out.data_ptr(), _stream(wf_layer.device)), "psb_tacaw_intensity")
     return out
 
 
@@ -334,7 +366,8 @@ def sum_pixels(x: torch.Tensor, mask: Optional[torch.Tensor] = None) -> torch.Te
     L = _lib.lib()
     fn = L.psb_sum_abs_pixels if x.dtype == torch.complex64 else L.psb_sum_pixels
     assert x.dtype in (torch.complex64, torch.float32)
-    _lib.check(fn(x.data_ptr(), m, rows, x.stride(0), npix, out.data_ptr(), _stream(x.device)), "psb_sum_pixels")
+    with _on(x.device):
+        _lib.check(fn(x.data_ptr(), m, rows, x.stride(0), npix, out.data_ptr(), _stream(x.device)), "psb_sum_pixels")
     return out
 
 
@@ -343,7 +376,8 @@ def sum_frames(x: torch.Tensor) -> torch.Tensor:
     G, T, npix = x.shape
     assert x.dtype == torch.float32 and x.is_contiguous()
     out = torch.empty((G, npix), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().psb_sum_frames(x.data_ptr(), G, T, npix, out.data_ptr(), _stream(x.device)), "psb_sum_frames")
+    with _on(x.device):
+        _lib.check(_lib.lib().psb_sum_frames(x.data_ptr(), G, T, npix, out.data_ptr(), _stream(x.device)), "psb_sum_frames")
     return out
 
 

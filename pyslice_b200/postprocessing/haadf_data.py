@@ -17,7 +17,11 @@ class HAADFData(WFData):
     def calculateADF(self, collection_angle: float = 45, preview: bool = False):
         """adf[i, j] = mean_frames sum_k |psi_k| * (|k| > collection_angle*1e-3/lambda) for the probe
         nearest to the i-th unique x / j-th unique y (haadf_data.py:43-65).  The mask uses the
-        float32 kxs/kys labels of the WFData, like the reference."""
+        float32 kxs/kys labels of the WFData, like the reference.
+
+        Frame-sharded runs (WFData.shard.world > 1: this process holds only its block of frames): the per-probe sums
+        are combined over ranks with one all-reduce and divided by the GLOBAL frame count, so every rank returns the
+        same image -- which makes this call a collective: every rank of the run must make it."""
         pp = np.asarray(self.probe_positions)
         self.xs = torch.as_tensor(sorted(set(pp[:, 0])))
         self.ys = torch.as_tensor(sorted(set(pp[:, 1])))
@@ -34,7 +38,14 @@ class HAADFData(WFData):
         wf = wf.to(device=dev, dtype=torch.complex64).contiguous()
         P, T, nx, ny = wf.shape
         sums = engine.sum_pixels(wf.reshape(P * T, nx * ny), mask.to(dev, torch.float32).reshape(-1))
-        per_probe = sums.reshape(P, T).mean(dim=1).cpu()
+        shard = getattr(self, "shard", None)
+        if shard is not None and shard.world > 1:
+            import torch.distributed as dist
+            tot = sums.reshape(P, T).sum(dim=1)
+            dist.all_reduce(tot)
+            per_probe = (tot / float(shard.total)).cpu()
+        else:
+            per_probe = sums.reshape(P, T).mean(dim=1).cpu()
         self.adf = torch.zeros((len(self.xs), len(self.ys)))
         for i, x in enumerate(self.xs.tolist()):
             for j, y in enumerate(self.ys.tolist()):

@@ -89,12 +89,15 @@ class TACAWData(WFData):
         if wf_layer.stride(3) != 1 or wf_layer.stride(2) != wf_layer.shape[3]:
             wf_layer = wf_layer.contiguous()
         shard = getattr(self, "shard", None)
+        timer = getattr(self, "_timer", None) or engine.NO_TIMER      # bench.py: CUDA-event phases
         self.row_range = (0, wf_layer.shape[2])
         if shard is not None and shard.world > 1:
             starts, counts = _row_split(wf_layer.shape[2], shard.world)
             self.row_range = (starts[shard.rank], starts[shard.rank] + counts[shard.rank])
-            wf_layer = frames_to_rows_all_to_all(wf_layer, shard)
-        self.intensity = engine.tacaw_intensity(wf_layer)
+            with timer.phase("all_to_all"):
+                wf_layer = frames_to_rows_all_to_all(wf_layer, shard)
+        with timer.phase("tacaw"):
+            self.intensity = engine.tacaw_intensity(wf_layer)
 
     # ---- helpers ---------------------------------------------------------------------------
     def _n_probes(self):
