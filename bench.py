@@ -191,13 +191,20 @@ def reference_root():
     return None
 
 
-def reference_sample_frames(wl):
-    """frames of the bounded sample: ~10-30 s of the reference's CPU work (it takes 1-2 s per plane-wave frame at 256^2 x 512
-    on 16 threads, ~20 s per frame at 1024^2, ~1 s per probe and frame at 512^2 x 67)"""
-    nx = wl["grid"][0]
-    if wl["probes"]:
-        return 1
-    return 6 if nx <= 256 else (2 if nx <= 512 else 1)
+_PILOT = {}
+
+
+def reference_sample_frames(wl, name, target_s=12.0):
+    """frames of the bounded sample, sized on the box itself: a two-frame pilot run of the reference (it also warms
+    torch's thread pool and the page cache) gives seconds per frame, and the sample is as many frames as fill ~target_s
+    of CPU work (the GPU hosts of this pool run a 256^2 x 512 plane-wave frame in ~0.3 s on 16 threads, the build
+    container takes 3.6 s on 8)"""
+    key = (name, wl["frames"])
+    if key not in _PILOT:
+        _, d = reference_torch_step(wl, name, n_frames=2)
+        _PILOT[key] = d["seconds"] / 2
+    per_frame = _PILOT[key]
+    return int(max(2, min(96, wl["frames"], round(target_s / max(per_frame, 1e-3)))))
 
 
 def reference_torch_step(wl, name, n_frames=None, n_probes_cap=16):
@@ -222,7 +229,7 @@ def reference_torch_step(wl, name, n_frames=None, n_probes_cap=16):
     except Exception:
         pass
     torch.set_num_threads(cores)
-    n = n_frames or reference_sample_frames(wl)
+    n = n_frames or reference_sample_frames(wl, name)
     traj = make_traj(wl, max(n, 2))            # TACAWData needs two time points for its frequency axis
     n = traj.n_frames
     pp = probe_positions(wl, traj.box_matrix)
@@ -324,10 +331,13 @@ def run_reference(args, wl, name):
         return
     vals, base = [], None
     total = args.warmup + args.steps
-    # every step is one bounded sample (~10-30 s); beyond 8 steps the sample shrinks to keep the run within minutes
-    n = reference_sample_frames(wl)
-    if total > 8:
-        n = max(2, n * 8 // total)
+    # every step is one bounded sample (~12 s of the reference's CPU work); beyond 8 steps the sample shrinks so that the
+    # whole run stays within a few minutes
+    try:
+        n = reference_sample_frames(wl, name, target_s=12.0 if total <= 8 else max(2.0, 100.0 / total))
+    except Exception as e:
+        print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"}))
+        return
     try:
         for i in range(total):
             v, base = reference_torch_step(wl, name, n_frames=n)
@@ -395,6 +405,7 @@ def main():
     ap.add_argument("--frames", type=int, default=0, help="override the workload's frame count (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the end-to-end arm (profiling runs)")
+    ap.add_argument("--no-clocks", action="store_true", help="do not sample clocks (diagnostic: NVML polls can hold up launches)")
     args = ap.parse_args()
     name = ALIASES.get(args.workload, args.workload)
     wl = dict(WORKLOADS[name])
@@ -509,7 +520,7 @@ def main():
     # the clock sampler is started BEFORE the warm-up (its start-up must not land inside the timed region); only the
     # samples taken during the timed region are reported
     sampler = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
         sampler.start()
         sampler.wait_ready()
     for _ in range(args.warmup):
@@ -521,15 +532,19 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     tac = None
+    marks = []
     for _ in range(args.steps):
-        del tac
-        tac = device_step(timer)
+        tac = device_step(timer)        # the previous result stays alive until the new one exists (as a caller's loop would)
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        marks.append(ev)
     e1.record()
     barrier()
     launches = engine.launch_count() - l0
     ms_dev = e0.elapsed_time(e1)
+    step_ms = [a.elapsed_time(b) for a, b in zip([e0] + marks[:-1], marks)]
     phases = timer.totals()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if rank == 0 and not args.no_clocks else None
     spectrum = tac.spectrum()          # touches the result (and checks the reducers run)
     assert np.isfinite(spectrum).all() and np.abs(spectrum).max() > 0
     del tac
@@ -579,7 +594,7 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
             "higher_is_better": True, "scaling": wl["scaling"], "vs_baseline": None, "dtype": "c64 (fp32 complex)",
             "data": "synthetic", "config": cfg,
-            "run": {"frames_per_batch": fb, "tacaw_wall_ms": ms_dev / args.steps},
+            "run": {"frames_per_batch": fb, "tacaw_wall_ms": ms_dev / args.steps, "step_ms": [round(x, 2) for x in step_ms]},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "phases_ms_per_step": {"potential": pot_ms / args.steps, "propagate_incl_exit_fft": prop_ms / args.steps,

@@ -1,4 +1,4 @@
-// Line FFTs of the fused slice-step kernels (fast_path.cu): N = 256 or 512 complex64 points held by
+// Line FFTs of the fused slice-step kernels (fast_path.cu): N = 256, 512 or 1024 complex64 points held by
 // T = N/16 threads, 16 points per thread in the strided register layout of fft_core.cuh
 // (thread j owns positions j + e*T), built for Blackwell's packed fp32 pipe:
 //
@@ -149,25 +149,34 @@ PSB_D void radix16_io(const In& in, const Out& out) {
 }
 
 // ---- per-thread persistent twiddles ---------------------------------------------------------------
-// N = 256 (radix 16 x 16):       w[t-1] = exp(-2*pi*i*j*t/256),  t = 1..15
-// N = 512 (radix 16 x 2 x 16):   w[t-1] = exp(-2*pi*i*j*t/512),  w2 = exp(-2*pi*i*(j & 15)/32)
+// N = 256  (radix 16 x 16):      w[t-1] = exp(-2*pi*i*j*t/256),  t = 1..15
+// N = 512  (radix 16 x 2 x 16):  w[t-1] = exp(-2*pi*i*j*t/512),  w2 = exp(-2*pi*i*(j & 15)/32)
 //                                (the radix-2 stage is folded into the last stage's loads, see line_fft)
+// N = 1024 (radix 16 x 4 x 16):  w[t-1] = exp(-2*pi*i*j*t/1024), w4[t-1] = exp(-2*pi*i*(j & 15)*t/64), t = 1..3
+//                                (the radix-4 stage runs in place in the exchange buffer, see line_fft)
 template <int N>
 struct Twiddles {
     cpx w[15];
     cpx w2;
+    cpx w4[3];
     // `staged` is the staged table of Plan<N, 16> built by tables.cu (layout: fft_core.cuh twiddle_offset)
     PSB_D void load(const float2* PSB_RESTRICT staged_f2, int j) {
         const cpx* PSB_RESTRICT staged = reinterpret_cast<const cpx*>(staged_f2);
-        static_assert(N == 256 || N == 512, "fast path line sizes");
+        static_assert(N == 256 || N == 512 || N == 1024, "fast path line sizes");
+        w2 = c_make(1.f, 0.f);
+        w4[0] = w4[1] = w4[2] = w2;
         if constexpr (N == 256) {
 #pragma unroll
             for (int t = 1; t < 16; ++t) w[t - 1] = staged[(t - 1) * 16 + j];
-            w2 = c_make(1.f, 0.f);
-        } else {
+        } else if constexpr (N == 512) {
             w2 = staged[j & 15];                                           // stage 2 block: R = 2, NS = 16
 #pragma unroll
             for (int t = 1; t < 16; ++t) w[t - 1] = staged[16 + (t - 1) * 32 + j];   // stage 3 block: NS = 32
+        } else {
+#pragma unroll
+            for (int t = 1; t < 4; ++t) w4[t - 1] = staged[(t - 1) * 16 + (j & 15)];  // stage 2 block: R = 4, NS = 16
+#pragma unroll
+            for (int t = 1; t < 16; ++t) w[t - 1] = staged[48 + (t - 1) * 64 + j];   // stage 3 block: NS = 64
         }
     }
 };
@@ -178,6 +187,7 @@ struct Twiddles {
 //               int at(int q)           element index of position q of this thread's line in that buffer
 //               void after_store(int i) all stores of exchange i visible to the line's threads
 //               void after_load(int i)  all loads of exchange i done (buffer reusable)
+//               void mid_sync(int i)    N = 1024: the in-place middle stage's stores to buffer i are visible
 // in(e)  -> the thread's input at position j + e*T (e = 0..15), called once per e while the first stage runs
 // out(e, value) <- the transform at position j + e*T, called once per e while the last stage runs
 // `hook()` runs right after the first exchange's stores are visible: by then every thread of the line's
@@ -199,10 +209,40 @@ PSB_D void line_fft(const In& in, const Out& out, const Twiddles<N>& tw, int j, 
         x.after_store(xi0);
         hook();
     }
+    if constexpr (N == 1024) {
+        // Middle stage (radix 4, NS = 16) IN PLACE in the exchange buffer.  In the Stockham indexing of fft_core.cuh the
+        // thread's butterfly m reads logical positions b + 256*t (b = j + 64*m, twiddle exp(-+2*pi*i*(b & 15)*t/64), and
+        // b & 15 = j & 15 for every m) and would write positions (b >> 4)*64 + (b & 15) + 16*u.  Instead output u is
+        // written back to the slot input t = u came from, so no thread touches another thread's words between the two
+        // barriers and one buffer serves both exchanges; the last stage then fetches logical position j + 64*t from the
+        // slot that holds it: thread (j & 15) + 16*(t & 3), butterfly t >> 2, output j >> 4, i.e. slot
+        // (j & 15) + 16*(t & 3) + 64*(t >> 2) + 256*(j >> 4)  (checked against numpy on the host, tests/test_fast_fft_host.py).
+        cpx* sm = x.buf(xi0);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const int b = j + 64 * m;
+            cpx a0 = sm[x.at(b)], a1 = sm[x.at(b + 256)], a2 = sm[x.at(b + 512)], a3 = sm[x.at(b + 768)];
+            a1 = DIR < 0 ? cmulp(a1, tw.w4[0]) : cmulcp(a1, tw.w4[0]);
+            a2 = DIR < 0 ? cmulp(a2, tw.w4[1]) : cmulcp(a2, tw.w4[1]);
+            a3 = DIR < 0 ? cmulp(a3, tw.w4[2]) : cmulcp(a3, tw.w4[2]);
+            radix4<DIR>(a0, a1, a2, a3);
+            sm[x.at(b)] = a0; sm[x.at(b + 256)] = a1; sm[x.at(b + 512)] = a2; sm[x.at(b + 768)] = a3;
+        }
+        x.mid_sync(xi0);
+    }
     // last stage: radix 16 with the thread's own twiddles; outputs come out in natural strided order
     const cpx* sl = x.buf(xi0);
     before_last();
-    if constexpr (N == 512) {
+    if constexpr (N == 1024) {
+        const int slot0 = (j & 15) + 256 * (j >> 4);
+        radix16_io<DIR>(
+            [&](int t) {
+                const cpx a = sl[x.at(slot0 + 16 * (t & 3) + 64 * (t >> 2))];
+                if (t == 0) return a;
+                return DIR < 0 ? cmulp(a, tw.w[t > 0 ? t - 1 : 0]) : cmulcp(a, tw.w[t > 0 ? t - 1 : 0]);
+            },
+            out);
+    } else if constexpr (N == 512) {
         // The radix-2 stage (NS = 16: butterfly pairs positions b and b + 256, twiddle exp(-+2*pi*i*(b & 15)/32) = w2)
         // is folded into the loads of the last stage instead of taking its own trip through shared memory: its
         // outputs land at (b/16)*32 + (b & 15) [sum] and + 16 [difference], and the last stage wants positions

@@ -1,4 +1,4 @@
-// Fused slice-step kernels for 256- and 512-point lines: the steady state of psb_propagate
+// Fused slice-step kernels for 256-, 512- and 1024-point lines: the steady state of psb_propagate
 // (reference: src/multislice/multislice.py:281-294, one loop iteration = one row pass + one column pass).
 //
 //   row pass   psi[x, ky] -> FFT_y( t_s[x, y] * IFFT_y( psi[x, ky] ) )                  (in place)
@@ -13,10 +13,11 @@
 //     read into registers, so L2/HBM latency hides behind the two line FFTs of the current tile;
 //   * row pass: a line (2 KB / 4 KB) belongs to the 16 / 32 lanes of ONE warp, so every warp is its own
 //     pipeline (private landing + exchange buffers, private mbarriers, __syncwarp only; no CTA barrier in
-//     the loop); 16 warps per SM;
-//   * column pass: a tile is 16 (8 for N = 512) adjacent columns so global segments are 128 B (64 B);
-//     256 threads, one CTA barrier per FFT stage exchange thanks to two alternating exchange buffers;
-//     2 CTAs per SM;
+//     the loop); 16 warps per SM.  A 1024-point line (8 KB) belongs to a PAIR of warps that synchronise on
+//     their own named barrier (bar.sync id, 64), eight such pipelines per SM;
+//   * column pass: a tile is 16 (8 for N = 512 and 1024) adjacent columns so global segments are 128 B (64 B);
+//     256 threads (512 for N = 1024), one CTA barrier per FFT stage exchange thanks to two alternating
+//     exchange buffers; 2 CTAs per SM (1 for N = 1024);
 //   * arithmetic is packed fp32x2 with per-thread persistent twiddles (fast_fft.cuh); the propagator
 //     factors sit in shared memory for the whole kernel.
 //
@@ -164,29 +165,41 @@ constexpr bool row_mode_steps(int mode) { return mode == R_STEP || mode == R_STE
 template <int N, int MODE = 0>
 struct RowCfg {
     static constexpr int T = N / 16;               // threads per line
-    static constexpr int LPW = 32 / T;             // lines per warp
+    static constexpr int kGroupThreads = T > 32 ? T : 32;      // threads that share buffers and synchronise: a warp, or a warp pair (N = 1024)
+    static constexpr int LPW = kGroupThreads / T;  // lines per group (unit of work)
     static constexpr int NP = N + N / 16;          // padded exchange pitch
     static constexpr int kTBufs = (MODE == 0) ? PSB_ROW_TBUFS : 1;
     static constexpr int kWarps = (MODE == 3) ? PSB_ROW_WARPS_PHASE : ((kTBufs == 1) ? 16 : 12);
     static constexpr int kThreads = 32 * kWarps;
-    static constexpr int kLand = LPW * N;          // float2 per landing buffer (4 KB)
+    static constexpr int kGroups = kThreads / kGroupThreads;
+    static constexpr int kLand = LPW * N;          // float2 per landing buffer (4 KB; 8 KB for N = 1024)
     static constexpr int kTLand = (MODE == 3) ? kLand / 2 : kLand;     // transmission rows of a unit: float phases or complex t
     static constexpr int kX = LPW * NP;
-    static constexpr int kWarpElems = kLand + kTBufs * kTLand + kX;
+    static constexpr int kWarpElems = kLand + kTBufs * kTLand + kX;    // per group
     static constexpr int kBars = 1 + kTBufs;
-    static constexpr size_t kSmem = (size_t)kWarps * kWarpElems * sizeof(float2) + kWarps * kBars * sizeof(uint64_t);
+    static constexpr size_t kSmem = (size_t)kGroups * kWarpElems * sizeof(float2) + kGroups * kBars * sizeof(uint64_t);
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
     static constexpr uint32_t kTBytes = kLand * (MODE == 3 ? sizeof(float) : sizeof(float2));     // transmission rows of a unit
+    static_assert(kThreads % kGroupThreads == 0 && (kGroupThreads == 32 || kGroups <= 15), "one named barrier per warp pair");
 };
+
+// barrier over the threads of one group: the warp itself, or the named barrier of a warp pair
+template <int THREADS>
+__device__ __forceinline__ void group_sync(int group) {
+    if constexpr (THREADS == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(THREADS) : "memory");
+}
 
 template <int N>
 struct RowXchg {
     cpx* x;
     int c;
+    int group;
     __device__ __forceinline__ cpx* buf(int) const { return x; }
     __device__ __forceinline__ int at(int q) const { return c * RowCfg<N>::NP + q + (q >> 4); }
-    __device__ __forceinline__ void after_store(int) const { __syncwarp(); }
-    __device__ __forceinline__ void after_load(int) const { __syncwarp(); }
+    __device__ __forceinline__ void after_store(int) const { group_sync<RowCfg<N>::kGroupThreads>(group); }
+    __device__ __forceinline__ void after_load(int) const { group_sync<RowCfg<N>::kGroupThreads>(group); }
+    __device__ __forceinline__ void mid_sync(int) const { group_sync<RowCfg<N>::kGroupThreads>(group); }
 };
 
 template <int N, int MODE>
@@ -194,12 +207,13 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
     using C = RowCfg<N, MODE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* sm = reinterpret_cast<cpx*>(smem_raw);
-    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // provably warp-uniform: bulk copies take uniform operands
-    const int lane = threadIdx.x & 31;
+    // group = the warp (or warp pair) that owns a unit; provably warp-uniform: bulk copies take uniform operands
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x / C::kGroupThreads), 0);
+    const int lane = threadIdx.x % C::kGroupThreads;
     cpx* land_psi = sm + (size_t)warp * C::kWarpElems;
     cpx* land_t = land_psi + C::kLand;                       // [kTBufs][kLand]
     cpx* xb = land_t + C::kTBufs * C::kTLand;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)C::kWarps * C::kWarpElems) + C::kBars * warp;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + (size_t)C::kGroups * C::kWarpElems) + C::kBars * warp;
     uint64_t* mb_psi = bars;
     uint64_t* mb_t = bars + 1;                               // [kTBufs]
 
@@ -212,15 +226,15 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
     const int c = lane / C::T, j = lane % C::T;
     fast::Twiddles<N> tw;
     tw.load(p.tw, j);
-    const RowXchg<N> xc{xb, c};
+    const RowXchg<N> xc{xb, c, warp};
     __syncthreads();
     pdl_wait();          // everything above reads constant tables only; the images come from the previous kernel
 
     const uint64_t stream_once = l2_policy_evict_first();
     // unit / image arithmetic in 32 bits with shifts: nx is 256 or 512 here, n_units < 2^31 (64-bit division is
     // a ~100-instruction subroutine, and it sat in every prefetch)
-    const int GW = (int)gridDim.x * C::kWarps;
-    int u = (int)blockIdx.x * C::kWarps + warp;
+    const int GW = (int)gridDim.x * C::kGroups;
+    int u = (int)blockIdx.x * C::kGroups + warp;
     const int n_units = (int)p.n_units;
     const int upi_shift = 31 - __clz(p.nx / C::LPW);          // log2(units per image)
     const int upi_mask = (1 << upi_shift) - 1;
@@ -341,16 +355,26 @@ struct ColPassParams {
 constexpr int kColXBufs = PSB_COL_XBUFS;
 constexpr int kColCtasPerSm = kColXBufs == 1 ? 3 : 2;
 
+// 1024-point columns: 512 threads and 8-column tiles in one CTA per SM (default), or 256 threads and 4-column tiles in
+// two CTAs per SM (-DPSB_COL1024_THREADS=256)
+#ifndef PSB_COL1024_THREADS
+#define PSB_COL1024_THREADS 512
+#endif
+
 template <int N>
 struct ColCfg {
     static constexpr int T = N / 16;
-    static constexpr int W = 256 / T;                                 // columns per tile: 16 (N=256), 8 (N=512)
-    static constexpr int kPadRows = (W == 8) ? N / 16 : 0;            // keeps 8-column rows conflict-free
-    static constexpr int kLand = N * W;                               // float2 (32 KB)
+    static constexpr int kThreads = N == 1024 ? PSB_COL1024_THREADS : 256;
+    static constexpr int kCtasPerSm = N == 1024 ? (kThreads == 512 ? 1 : 2) : kColCtasPerSm;
+    static constexpr int W = kThreads / T;                            // columns per tile: 16 (N=256), 8 (N=512, 1024), 4 (1024, 256 threads)
+    static constexpr int kPadRows = (W < 16) ? N / 16 : 0;            // keeps narrow rows conflict-free
+    static constexpr int kLand = N * W;                               // float2 (32 KB; 64 KB for N = 1024)
     static constexpr int kX = (N + kPadRows) * W;
-    static constexpr size_t kSmem = (size_t)(kLand + kColXBufs * kX + N) * sizeof(float2) + 2 * sizeof(uint64_t);      // + NY*8 for Py, added at launch
+    static constexpr bool kTablesInSmem = N < 1024;                   // Px, Py staged per CTA (1024: read through L1)
+    static constexpr size_t kSmem = (size_t)(kLand + kColXBufs * kX + (kTablesInSmem ? N : 0)) * sizeof(float2) + 2 * sizeof(uint64_t);      // + NY*8 for Py, added at launch
     static constexpr int kBoxRows = 256;                              // TMA box limit per dimension
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
+    static constexpr size_t smem_for(int ny) { return kSmem + (kTablesInSmem ? (size_t)ny * sizeof(float2) : 0); }
 };
 
 // Exchange policy of the column pass: two alternating buffers, one CTA barrier per exchange.  The first
@@ -367,7 +391,7 @@ struct ColXchg {
     int hook_i;                  // index of the tile's first exchange
     __device__ __forceinline__ cpx* buf(int i) const { return (kColXBufs == 2 && (i & 1)) ? b1 : b0; }
     __device__ __forceinline__ int at(int q) const {
-        return (ColCfg<N>::W == 8 ? q + (q >> 4) : q) * ColCfg<N>::W + c;
+        return (ColCfg<N>::W < 16 ? q + (q >> 4) : q) * ColCfg<N>::W + c;
     }
     __device__ __forceinline__ void after_store(int i) const {
         __syncthreads();
@@ -381,20 +405,21 @@ struct ColXchg {
     __device__ __forceinline__ void after_load(int) const {
         if (kColXBufs == 1) __syncthreads();
     }
+    __device__ __forceinline__ void mid_sync(int) const { __syncthreads(); }
 };
 
 enum ColMode { C_PROPAGATE = 0, C_INVERSE = 1 };
 
 template <int N, int NY, int MODE>
-__global__ void __launch_bounds__(256, kColCtasPerSm) fast_cols_kernel(const __grid_constant__ CUtensorMap tmap, const ColPassParams p) {
+__global__ void __launch_bounds__(ColCfg<N>::kThreads, ColCfg<N>::kCtasPerSm) fast_cols_kernel(const __grid_constant__ CUtensorMap tmap, const ColPassParams p) {
     using C = ColCfg<N>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* land = reinterpret_cast<cpx*>(smem_raw);
     cpx* xb0 = land + C::kLand;
     cpx* xb1 = xb0 + (kColXBufs - 1) * C::kX;
     cpx* spx = xb1 + C::kX;
-    cpx* spy = spx + N;
-    uint64_t* mb = reinterpret_cast<uint64_t*>(spy + NY);
+    cpx* spy = spx + (C::kTablesInSmem ? N : 0);
+    uint64_t* mb = reinterpret_cast<uint64_t*>(spy + (C::kTablesInSmem ? NY : 0));
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -402,10 +427,12 @@ __global__ void __launch_bounds__(256, kColCtasPerSm) fast_cols_kernel(const __g
         mbar_init_fence();
     }
     pdl_trigger();
-    if constexpr (MODE == C_PROPAGATE) {
-        for (int i = tid; i < N; i += 256) spx[i] = reinterpret_cast<const cpx*>(p.px)[i];
-        for (int i = tid; i < NY; i += 256) spy[i] = reinterpret_cast<const cpx*>(p.py)[i];
+    if constexpr (MODE == C_PROPAGATE && C::kTablesInSmem) {
+        for (int i = tid; i < N; i += C::kThreads) spx[i] = reinterpret_cast<const cpx*>(p.px)[i];
+        for (int i = tid; i < NY; i += C::kThreads) spy[i] = reinterpret_cast<const cpx*>(p.py)[i];
     }
+    const cpx* gpx = reinterpret_cast<const cpx*>(p.px);
+    const cpx* gpy = reinterpret_cast<const cpx*>(p.py);
 
     const int c = tid % C::W, j = tid / C::W;
     fast::Twiddles<N> tw;
@@ -439,9 +466,13 @@ __global__ void __launch_bounds__(256, kColCtasPerSm) fast_cols_kernel(const __g
             cpx v[16];
             // * Py[ky] -> FFT_x -> * Px[kx] -> IFFT_x
             xc.hook_i = 0;
-            const cpx pyc = spy[(int)(tile % kTilesPerImg) * C::W + c];
+            const int col = (int)(tile % kTilesPerImg) * C::W + c;
+            const cpx pyc = C::kTablesInSmem ? spy[col] : __ldg(gpy + col);
             fast::line_fft<N, -1>([&](int e) { return fast::cmulp(lp[e * C::T * C::W], pyc); },
-                                  [&](int e, cpx a) { v[e] = fast::cmulp(a, spx[j + e * C::T]); }, tw, j, xc, 0);
+                                  [&](int e, cpx a) {
+                                      v[e] = fast::cmulp(a, C::kTablesInSmem ? spx[j + e * C::T] : __ldg(gpx + j + e * C::T));
+                                  },
+                                  tw, j, xc, 0);
             xc.next_c0 = -1;
             fast::line_fft<N, +1>([&](int e) { return v[e]; }, [&](int e, cpx a) { dst[e * C::T * NY] = a; }, tw, j, xc,
                                   fast::exchanges<N>());
@@ -506,7 +537,7 @@ int rows_go(const RowPassParams& p, cudaStream_t s) {
     static rt::PerDeviceOnce once;
     int rc0 = once.run([] { return ensure_smem(fast_rows_kernel<N, MODE>, C::kSmem, "fast row pass"); });
     if (rc0 != PSB_OK) return rc0;
-    long long want = (p.n_units + C::kWarps - 1) / C::kWarps;
+    long long want = (p.n_units + C::kGroups - 1) / C::kGroups;
     const int sms = rt::sm_count();
     const int grid = (int)(want < sms ? want : sms);
     cudaError_t e = pdl_launch(fast_rows_kernel<N, MODE>, dim3(grid), dim3(C::kThreads), C::kSmem, s, p);
@@ -519,7 +550,7 @@ template <int N, int NY, int MODE>
 int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const float2* tw, cudaStream_t s) {
     using C = ColCfg<N>;
     static rt::PerDeviceOnce once;
-    int rc0 = once.run([] { return ensure_smem(fast_cols_kernel<N, NY, MODE>, C::kSmem + NY * sizeof(float2), "fast column pass"); });
+    int rc0 = once.run([] { return ensure_smem(fast_cols_kernel<N, NY, MODE>, C::smem_for(NY), "fast column pass"); });
     if (rc0 != PSB_OK) return rc0;
     // the tensor map depends on the buffer and the batch size only: keep the last one of this host thread (a map is
     // plain host data passed by value at launch, so a per-thread cache needs no lock and cannot cross devices: device
@@ -536,9 +567,9 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const fl
     ColPassParams p;
     p.psi = psi; p.px = px; p.py = py; p.tw = tw;
     p.n_tiles = (long long)n_img * (NY / C::W);
-    const long long slots = (long long)kColCtasPerSm * rt::sm_count();
+    const long long slots = (long long)C::kCtasPerSm * rt::sm_count();
     const int grid = (int)(p.n_tiles < slots ? p.n_tiles : slots);
-    cudaError_t e = pdl_launch(fast_cols_kernel<N, NY, MODE>, dim3(grid), dim3(256), C::kSmem + NY * sizeof(float2), s, map, p);
+    cudaError_t e = pdl_launch(fast_cols_kernel<N, NY, MODE>, dim3(grid), dim3(C::kThreads), C::smem_for(NY), s, map, p);
     ++launch_counter();
     if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("fast column pass launch: ") + cudaGetErrorString(e));
     return PSB_OK;
@@ -550,73 +581,76 @@ void fast_path_enable(int level) { g_fast_enabled.store(level <= 0 ? 0 : 1); }
 bool fast_path_enabled() { return g_fast_enabled.load() != 0; }
 int fast_path_level() { return g_fast_enabled.load(); }
 
+static bool fast_line(int n) { return n == 256 || n == 512 || n == 1024; }
+
 bool fast_slice_supported(int nx, int ny) {
     if (!g_fast_enabled.load()) return false;
-    return (nx == 256 || nx == 512) && (ny == 256 || ny == 512);
+    return fast_line(nx) && fast_line(ny);
+}
+
+// row passes: dispatch on the line length ny and fill in the unit count
+template <int MODE>
+static int rows_dispatch(RowPassParams& p, int n_img, int nx, int ny, cudaStream_t s) {
+    int rc = twiddles_for(ny, &p.tw, s);
+    if (rc != PSB_OK) return rc;
+    p.nx = nx;
+    if (ny == 256) {
+        p.n_units = (long long)n_img * nx / RowCfg<256, MODE>::LPW;
+        return rows_go<256, MODE>(p, s);
+    }
+    if (ny == 512) {
+        p.n_units = (long long)n_img * nx / RowCfg<512, MODE>::LPW;
+        return rows_go<512, MODE>(p, s);
+    }
+    if (ny == 1024) {
+        p.n_units = (long long)n_img * nx / RowCfg<1024, MODE>::LPW;
+        return rows_go<1024, MODE>(p, s);
+    }
+    return fail(PSB_ERR_UNSUPPORTED, "fast row pass: unsupported line length");
 }
 
 int launch_fast_rows(float2* psi, int n_img, int nx, int ny, const float2* t_slice, long long t_frame_stride,
                      int probes, cudaStream_t s) {
     RowPassParams p;
     std::memset(&p, 0, sizeof(p));
-    p.psi = psi; p.t = t_slice; p.t_frame_stride = t_frame_stride; p.probes = probes; p.nx = nx;
-    int rc = twiddles_for(ny, &p.tw, s);
-    if (rc != PSB_OK) return rc;
-    if (ny == 256) {
-        p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
-        return rows_go<256, R_STEP>(p, s);
-    }
-    p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
-    return rows_go<512, R_STEP>(p, s);
+    p.psi = psi; p.t = t_slice; p.t_frame_stride = t_frame_stride; p.probes = probes;
+    return rows_dispatch<R_STEP>(p, n_img, nx, ny, s);
 }
 
 int launch_fast_rows_phase(float2* psi, int n_img, int nx, int ny, const float* phase_slice, long long t_frame_stride,
                            int probes, cudaStream_t s) {
     RowPassParams p;
     std::memset(&p, 0, sizeof(p));
-    p.psi = psi; p.t = reinterpret_cast<const float2*>(phase_slice); p.t_frame_stride = t_frame_stride; p.probes = probes; p.nx = nx;
-    int rc = twiddles_for(ny, &p.tw, s);
-    if (rc != PSB_OK) return rc;
-    if (ny == 256) {
-        p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
-        return rows_go<256, R_STEP_PHASE>(p, s);
-    }
-    p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
-    return rows_go<512, R_STEP_PHASE>(p, s);
+    p.psi = psi; p.t = reinterpret_cast<const float2*>(phase_slice); p.t_frame_stride = t_frame_stride; p.probes = probes;
+    return rows_dispatch<R_STEP_PHASE>(p, n_img, nx, ny, s);
 }
 
 int launch_fast_rows_phase_out(float2* pairs, int n_img, int nx, int ny, float scale, float sigma, float* phase_out,
                                int pair_count, int pair_nz, int pair_begin, cudaStream_t s) {
     RowPassParams p;
     std::memset(&p, 0, sizeof(p));
-    p.psi = pairs; p.nx = nx; p.probes = 1;
+    p.psi = pairs; p.probes = 1;
     p.v_out = phase_out; p.scale = scale; p.sigma = sigma;
     p.pair_count = pair_count; p.pair_nz = pair_nz; p.pair_begin = pair_begin;
-    int rc = twiddles_for(ny, &p.tw, s);
-    if (rc != PSB_OK) return rc;
-    if (ny == 256) {
-        p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
-        return rows_go<256, R_PHASE>(p, s);
-    }
-    p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
-    return rows_go<512, R_PHASE>(p, s);
+    return rows_dispatch<R_PHASE>(p, n_img, nx, ny, s);
 }
 
 int launch_fast_rows_transmit(float2* pairs, int n_img, int nx, int ny, float scale, float sigma, float2* t_out,
                               float* v_out, int pair_count, int pair_nz, int pair_begin, cudaStream_t s) {
     RowPassParams p;
     std::memset(&p, 0, sizeof(p));
-    p.psi = pairs; p.nx = nx; p.probes = 1;
+    p.psi = pairs; p.probes = 1;
     p.t_out = t_out; p.v_out = v_out; p.scale = scale; p.sigma = sigma;
     p.pair_count = pair_count; p.pair_nz = pair_nz; p.pair_begin = pair_begin;
-    int rc = twiddles_for(ny, &p.tw, s);
-    if (rc != PSB_OK) return rc;
-    if (ny == 256) {
-        p.n_units = (long long)n_img * nx / RowCfg<256>::LPW;
-        return rows_go<256, R_TRANSMIT>(p, s);
-    }
-    p.n_units = (long long)n_img * nx / RowCfg<512>::LPW;
-    return rows_go<512, R_TRANSMIT>(p, s);
+    return rows_dispatch<R_TRANSMIT>(p, n_img, nx, ny, s);
+}
+
+template <int MODE, int N>
+static int cols_dispatch_ny(float2* psi, int n_img, int ny, const float2* px, const float2* py, const float2* tw, cudaStream_t s) {
+    if (ny == 256) return cols_go<N, 256, MODE>(psi, n_img, px, py, tw, s);
+    if (ny == 512) return cols_go<N, 512, MODE>(psi, n_img, px, py, tw, s);
+    if (ny == 1024) return cols_go<N, 1024, MODE>(psi, n_img, px, py, tw, s);
+    return fail(PSB_ERR_UNSUPPORTED, "fast column pass: unsupported grid");
 }
 
 template <int MODE>
@@ -624,10 +658,9 @@ static int cols_dispatch(float2* psi, int n_img, int nx, int ny, const float2* p
     const float2* tw = nullptr;
     int rc = twiddles_for(nx, &tw, s);
     if (rc != PSB_OK) return rc;
-    if (nx == 256 && ny == 256) return cols_go<256, 256, MODE>(psi, n_img, px, py, tw, s);
-    if (nx == 256 && ny == 512) return cols_go<256, 512, MODE>(psi, n_img, px, py, tw, s);
-    if (nx == 512 && ny == 256) return cols_go<512, 256, MODE>(psi, n_img, px, py, tw, s);
-    if (nx == 512 && ny == 512) return cols_go<512, 512, MODE>(psi, n_img, px, py, tw, s);
+    if (nx == 256) return cols_dispatch_ny<MODE, 256>(psi, n_img, ny, px, py, tw, s);
+    if (nx == 512) return cols_dispatch_ny<MODE, 512>(psi, n_img, ny, px, py, tw, s);
+    if (nx == 1024) return cols_dispatch_ny<MODE, 1024>(psi, n_img, ny, px, py, tw, s);
     return fail(PSB_ERR_UNSUPPORTED, "fast column pass: unsupported grid");
 }
 

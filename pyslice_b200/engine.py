@@ -245,7 +245,7 @@ def chunk_images(plan: SlicePlan, n_frames: int) -> int:
 
 
 def phase_format_supported(plan: SlicePlan) -> bool:
-    """True when the transmission stack of this grid may be kept as float32 phases (fused kernels: 256 / 512 points)."""
+    """True when the transmission stack of this grid may be kept as float32 phases (fused kernels: 256 / 512 / 1024 points)."""
     return bool(_lib.lib().psb_phase_format_supported(plan.nx, plan.ny))
 
 
@@ -416,7 +416,7 @@ def batch_sizes(plan: SlicePlan, n_probes: int, n_frames: int):
     img = plan.nx * plan.ny * 8
     per_frame_t = plan.nz * img
     max_imgs = max(1, PSI_BATCH_BYTES // img)
-    slots = 2 * _sm_count()
+    slots = (1 if plan.nx >= 1024 else 2) * _sm_count()          # CTAs of the column pass that run side by side
     tiles_per_img = max(1, plan.ny // (8 if plan.nx >= 512 else 16))
     if n_probes >= max_imgs:
         fb, pb = 1, _fill_images(max_imgs, tiles_per_img, slots)

@@ -20,6 +20,7 @@ struct HostXchg {
     int at(int q) const { return q; }
     void after_store(int) const { bar->arrive_and_wait(); }
     void after_load(int) const {}          // alternating buffers: the next exchange's barrier orders the reuse
+    void mid_sync(int) const { bar->arrive_and_wait(); }
 };
 
 template <int N>
@@ -33,10 +34,15 @@ std::vector<float2> staged_table() {
     if (N == 256) {
         for (int tt = 1; tt < 16; ++tt)
             for (int k = 0; k < 16; ++k) t.push_back(w((long long)k * tt, 256));
-    } else {
+    } else if (N == 512) {
         for (int k = 0; k < 16; ++k) t.push_back(w(k, 32));
         for (int tt = 1; tt < 16; ++tt)
             for (int k = 0; k < 32; ++k) t.push_back(w((long long)k * tt, 512));
+    } else {
+        for (int tt = 1; tt < 4; ++tt)
+            for (int k = 0; k < 16; ++k) t.push_back(w((long long)k * tt, 64));
+        for (int tt = 1; tt < 16; ++tt)
+            for (int k = 0; k < 64; ++k) t.push_back(w((long long)k * tt, 1024));
     }
     return t;
 }
@@ -74,6 +80,8 @@ extern "C" int fast_fft_line(int N, int dir, const float* in, float* out, int re
     else if (N == 256) run_line<256, +1>(i2, o2, reps);
     else if (N == 512 && dir < 0) run_line<512, -1>(i2, o2, reps);
     else if (N == 512) run_line<512, +1>(i2, o2, reps);
+    else if (N == 1024 && dir < 0) run_line<1024, -1>(i2, o2, reps);
+    else if (N == 1024) run_line<1024, +1>(i2, o2, reps);
     else return -1;
     return 0;
 }

@@ -284,6 +284,11 @@ FAST_CASES = [
     ((51.15, 51.15, 3.1), 2, 30.0, (512, 512)),
     ((25.55, 51.15, 4.1), 1, 0.0, (256, 512)),
     ((51.15, 25.55, 4.1), 2, 20.0, (512, 256)),
+    # 1024-point lines (warp-pair row pipelines, radix 16 x 4 x 16 with the in-place middle stage, 8-column tiles)
+    ((102.35, 102.35, 2.6), 2, 30.0, (1024, 1024)),
+    ((102.35, 25.55, 3.1), 1, 0.0, (1024, 256)),
+    ((25.55, 102.35, 3.1), 2, 20.0, (256, 1024)),
+    ((51.15, 102.35, 2.1), 1, 0.0, (512, 1024)),
 ]
 
 
@@ -321,6 +326,9 @@ def test_fused_slice_step_vs_generic_and_oracle(box, n_probes, aperture, grid):
     ((51.15, 25.55, 3.2), 500, (14,), 3),         # 512 x 256
     ((25.55, 51.15, 2.2), 700, (5, 7), 2),        # 256 x 512
     ((51.15, 51.15, 1.2), 400, (6,), 2),          # 512 x 512
+    ((102.35, 102.35, 1.7), 1500, (14, 6), 2),    # 1024 x 1024 (3 slices: last pair half empty)
+    ((102.35, 51.15, 1.2), 600, (14,), 2),        # 1024 x 512
+    ((25.55, 102.35, 1.2), 500, (5, 7), 2),       # 256 x 1024
     ((25.55, 25.55, 1.6), 6000, (14, 79), 2),     # 256 x 256, ~1500 atoms per slice: segments of many ring blocks
     ((25.55, 25.55, 40.3), 300, (6, 14), 4),      # 256 x 256, 81 slices, ~2 atoms per (slice, type): empty segments
     ((6.35, 6.35, 4.1), 200, (6, 14, 31), 3),     # 64 x 64: pipelined structure factor + generic transforms
@@ -513,7 +521,8 @@ def test_tacaw_tiled_kernel_vs_generic(T, nx, ny, P):
     assert np.array_equal(out[1], engine.tacaw_intensity(x).cpu().numpy())  # deterministic
 
 
-@pytest.mark.parametrize("box,grid", [((25.55, 25.55, 12.2), (256, 256)), ((51.15, 25.55, 3.1), (512, 256))])
+@pytest.mark.parametrize("box,grid", [((25.55, 25.55, 12.2), (256, 256)), ((51.15, 25.55, 3.1), (512, 256)),
+                                      ((102.35, 102.35, 2.6), (1024, 1024))])
 def test_phase_stack_equals_complex_stack(box, grid):
     """The float32 phase format of the transmission stack (psb_build_phase / psb_propagate_phase: sigma*V stored,
     exp(i*phase) evaluated inside the fused row pass) against the complex64 stack: exit waves of the same probes."""

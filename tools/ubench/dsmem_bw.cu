@@ -28,13 +28,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_dsmem(int mode, int reps, float
     for (int r = 0; r < reps; ++r) {
         unsigned peer = mode == 0 ? rank : (mode == 3 ? (rank + 1 + r % (cs > 1 ? cs - 1 : 1)) % cs : (rank + 1) % cs);
         float4* p = cluster.map_shared_rank(mine, peer);
+        const int o = (r * 97) & (n4 - 1);          // the offset changes every repetition: nothing can be hoisted out of the loop
         if (mode == 2) {
 #pragma unroll 8
-            for (int i = threadIdx.x; i < n4; i += kThreads) p[i] = make_float4(acc, r, i, 0.f);
+            for (int i = threadIdx.x; i < n4; i += kThreads) p[(i + o) & (n4 - 1)] = make_float4(acc, r, i, 0.f);
         } else {
 #pragma unroll 8
             for (int i = threadIdx.x; i < n4; i += kThreads) {
-                float4 v = p[i];
+                const float4 v = p[(i + o) & (n4 - 1)];
                 acc += v.x + v.y + v.z + v.w;
             }
         }
