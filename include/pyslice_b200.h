@@ -110,6 +110,41 @@ int psb_propagate_phase(const psb_c64* probes, const float* phase, psb_c64* t0, 
                         long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
                         void* stream);
 
+/* The general form of the two calls above, one descriptor instead of 18 positional arguments, plus two output modes the
+ * multi-GPU run and the STEM detectors need.  `struct_bytes` = sizeof(psb_propagate_desc) (checked).
+ *   t / phase      exactly one is non-NULL: complex64 stack, or float32 phase stack (then t0_scratch (F, nx, ny) is required)
+ *   mode 0, 1      as psb_propagate
+ *   slab_world > 1 (mode 1): wf_out is laid out for the frames -> kx-rows all-to-all that precedes the time FFT
+ *                  (replaces the pack pass around calculators.py:285-290,185-186): the shifted kx rows are
+ *                  split into slab_world contiguous blocks (the first nx % slab_world blocks hold one row more), and
+ *                  wf_out[block h][layer][frame][probe][row in block][ky'] with slab_layers x slab_frames x slab_probes
+ *                  planes per block; this call fills frames [frame0, frame0 + n_frames) and probes [probe0, probe0 + n_probes).
+ *                  Each block is one contiguous message.  stride_* are ignored.
+ *   mode 2         detector sums only (haadf_data.py:43-65 without the cube): at every layer tap the shifted k-space image
+ *                  goes to det_scratch (n_frames*n_probes, nx, ny) and det_out[layer*det_stride_layer +
+ *                  (probe0 + probe)*det_stride_probe + frame0 + frame] = sum_k |psi_k| * det_mask[kx', ky'] (float64). */
+typedef struct psb_propagate_desc {
+    int struct_bytes;
+    int mode, layer_every;
+    int n_frames, n_probes, nz, nx, ny;
+    const psb_c64* probes;
+    const psb_c64* t;
+    const float* phase;
+    psb_c64* t0_scratch;
+    const psb_c64* prop_x;
+    const psb_c64* prop_y;
+    psb_c64* psi_work;
+    psb_c64* wf_out;
+    long long stride_probe, stride_frame, stride_layer;
+    int slab_world, slab_layers, slab_frames, slab_probes, frame0, probe0;
+    const float* det_mask;
+    double* det_out;
+    long long det_stride_layer, det_stride_probe;
+    psb_c64* det_scratch;
+    void* stream;
+} psb_propagate_desc;
+int psb_propagate_ex(const psb_propagate_desc* desc);
+
 /* ---- TACAW: tacaw_data.py:89-104.  intensity[p, w, pix] = |fftshift_t FFT_t(psi - mean_t psi)|^2
  * wf element (p, f, pix) at wf[p*stride_probe + f*stride_frame + pix]; intensity (P, T, npix) float32. */
 int psb_tacaw_intensity(const psb_c64* wf, long long stride_probe, long long stride_frame, int n_probes,

@@ -25,6 +25,19 @@ _LL = C.c_longlong
 _F = C.c_float
 _D = C.c_double
 
+class PropagateDesc(C.Structure):
+    """`psb_propagate_desc` of include/pyslice_b200.h (field for field)."""
+    _fields_ = [
+        ("struct_bytes", _I), ("mode", _I), ("layer_every", _I),
+        ("n_frames", _I), ("n_probes", _I), ("nz", _I), ("nx", _I), ("ny", _I),
+        ("probes", _P), ("t", _P), ("phase", _P), ("t0_scratch", _P), ("prop_x", _P), ("prop_y", _P), ("psi_work", _P),
+        ("wf_out", _P), ("stride_probe", _LL), ("stride_frame", _LL), ("stride_layer", _LL),
+        ("slab_world", _I), ("slab_layers", _I), ("slab_frames", _I), ("slab_probes", _I), ("frame0", _I), ("probe0", _I),
+        ("det_mask", _P), ("det_out", _P), ("det_stride_layer", _LL), ("det_stride_probe", _LL), ("det_scratch", _P),
+        ("stream", _P),
+    ]
+
+
 _SIGNATURES = {
     "psb_version": (C.c_int, []),
     "psb_last_error": (C.c_char_p, []),
@@ -41,6 +54,7 @@ _SIGNATURES = {
     "psb_phase_format_supported": (C.c_int, [_I, _I]),
     "psb_propagate_phase": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _LL, _LL, _LL, _I, _P]),
     "psb_propagate": (C.c_int, [_P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _I, _P, _LL, _LL, _LL, _I, _P]),
+    "psb_propagate_ex": (C.c_int, [C.POINTER(PropagateDesc)]),
     "psb_tacaw_intensity": (C.c_int, [_P, _LL, _LL, _I, _I, _LL, _P, _P]),
     "psb_sum_pixels": (C.c_int, [_P, _P, _I, _LL, _LL, _P, _P]),
     "psb_sum_abs_pixels": (C.c_int, [_P, _P, _I, _LL, _LL, _P, _P]),

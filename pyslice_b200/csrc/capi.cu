@@ -295,24 +295,56 @@ int psb_shift_probes(const psb_c64* base_k, const psb_c64* ramp_x, const psb_c64
     return launch_line_pass(PASS_INV_ROWS, p, n_probes, s);
 }
 
-// phase != nullptr: the stack holds float32 phases; t0 (n_frames, nx, ny) receives exp(i*phase) of slice 0 for the
-// generic first pass, every later slice is evaluated inside the fused row pass
-static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* phase, psb_c64* t0, int n_frames, int n_probes,
-                          int nz, int nx, int ny, const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode,
-                          psb_c64* wf_out, long long stride_probe, long long stride_frame, long long stride_layer,
-                          int layer_every, void* stream) {
-    if (!probes || (!t && !phase) || !prop_x || !prop_y || !psi_work) return fail(PSB_ERR_INVALID, "psb_propagate: null pointer");
-    if (phase && !t0) return fail(PSB_ERR_INVALID, "psb_propagate_phase: t0 scratch required");
-    if (mode != 0 && mode != 1) return fail(PSB_ERR_INVALID, "psb_propagate: mode must be 0 or 1");
-    if (mode == 1 && !wf_out) return fail(PSB_ERR_INVALID, "psb_propagate: wf_out required in mode 1");
-    if (n_frames < 0 || n_probes < 1 || nz < 1 || nx < 1 || ny < 1 || layer_every < 0)
+static int sum_pixels_impl(const float* in, const float2* cin, const float* mask, int rows, long long row_stride,
+                           long long npix, double* out, void* stream, int row_mod = 0, long long out_stride_mod = 0,
+                           long long out_stride_div = 0);
+
+// desc.phase != nullptr: the stack holds float32 phases; t0_scratch (n_frames, nx, ny) receives exp(i*phase) of slice 0 for
+// the generic first pass, every later slice is evaluated inside the fused row pass
+int psb_propagate_ex(const psb_propagate_desc* dp) {
+    if (!dp || dp->struct_bytes != (int)sizeof(psb_propagate_desc))
+        return fail(PSB_ERR_INVALID, "psb_propagate_ex: descriptor size mismatch (header / library version skew)");
+    const psb_propagate_desc& d = *dp;
+    const psb_c64* t = d.t;
+    const float* phase = d.phase;
+    const int n_frames = d.n_frames, n_probes = d.n_probes, nz = d.nz, nx = d.nx, ny = d.ny, mode = d.mode;
+    if (!d.probes || (!t && !phase) || (t && phase) || !d.prop_x || !d.prop_y || !d.psi_work)
+        return fail(PSB_ERR_INVALID, "psb_propagate: null pointer (or both t and phase given)");
+    if (phase && !d.t0_scratch) return fail(PSB_ERR_INVALID, "psb_propagate_phase: t0 scratch required");
+    if (mode < 0 || mode > 2) return fail(PSB_ERR_INVALID, "psb_propagate: mode must be 0, 1 or 2");
+    if (mode == 1 && !d.wf_out) return fail(PSB_ERR_INVALID, "psb_propagate: wf_out required in mode 1");
+    if (mode == 2 && (!d.det_mask || !d.det_out || !d.det_scratch))
+        return fail(PSB_ERR_INVALID, "psb_propagate: det_mask, det_out and det_scratch required in mode 2");
+    if (n_frames < 0 || n_probes < 1 || nz < 1 || nx < 1 || ny < 1 || d.layer_every < 0)
         return fail(PSB_ERR_INVALID, "psb_propagate: bad sizes");
+    const bool slabs = mode == 1 && d.slab_world > 1;
+    if (slabs && (d.slab_world > nx || d.slab_layers < 1 || d.slab_frames < 1 || d.slab_probes < 1 || d.frame0 < 0 || d.probe0 < 0 ||
+                  d.frame0 + n_frames > d.slab_frames || d.probe0 + n_probes > d.slab_probes))
+        return fail(PSB_ERR_INVALID, "psb_propagate: bad slab layout");
     const long long n_img_ll = (long long)n_frames * n_probes;
     if (n_img_ll == 0) return PSB_OK;
-    if (n_img_ll > 65535) return fail(PSB_ERR_UNSUPPORTED, "psb_propagate: frames*probes per call must be <= 65535");
-    const int n_img = (int)n_img_ll;
-    cudaStream_t s = as_stream(stream);
+    cudaStream_t s = as_stream(d.stream);
     const long long img = (long long)nx * ny;
+    // the generic passes put the image index in gridDim.y: larger batches go through in slices of whole frames
+    if (n_img_ll > 65535) {
+        const int fmax = 65535 / n_probes;
+        if (fmax < 1) return fail(PSB_ERR_UNSUPPORTED, "psb_propagate: more than 65535 probes per call");
+        for (int f0 = 0; f0 < n_frames; f0 += fmax) {
+            psb_propagate_desc part = d;
+            part.n_frames = n_frames - f0 < fmax ? n_frames - f0 : fmax;
+            if (t) part.t = t + (long long)f0 * nz * img;
+            if (phase) part.phase = phase + (long long)f0 * nz * img;
+            if (mode == 1 && !slabs) part.wf_out = d.wf_out + (long long)f0 * d.stride_frame;
+            part.psi_work = d.psi_work + (long long)f0 * n_probes * img;          // mode 0 leaves its result there
+            part.frame0 = d.frame0 + f0;
+            int rc = psb_propagate_ex(&part);
+            if (rc != PSB_OK) return rc;
+        }
+        return PSB_OK;
+    }
+    const int n_img = (int)n_img_ll;
+    const int layer_every = d.layer_every;
+    psb_c64* psi_work = d.psi_work;
 
     PassParams row = base_params();
     row.dst = f2(psi_work); row.dst_img_stride = img;
@@ -323,14 +355,22 @@ static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* 
     PassParams col = base_params();
     col.src = f2(psi_work); col.dst = f2(psi_work); col.src_img_stride = img; col.dst_img_stride = img;
     cols_geometry(col, nx, ny);
-    col.sep_p = f2(prop_x); col.sep_l = f2(prop_y);
+    col.sep_p = f2(d.prop_x); col.sep_l = f2(d.prop_y);
 
     PassParams ex = base_params();
     ex.src = f2(psi_work); ex.src_img_stride = img;
     cols_geometry(ex, nx, ny);
     ex.probes = n_probes;
-    ex.out_stride_probe = stride_probe; ex.out_stride_frame = stride_frame;
+    ex.out_stride_probe = d.stride_probe; ex.out_stride_frame = d.stride_frame;
     ex.out_elem_stride = ny; ex.out_line_stride = 1;
+    if (slabs) {
+        ex.slab_world = d.slab_world; ex.slab_base = nx / d.slab_world; ex.slab_rem = nx % d.slab_world;
+        ex.slab_planes = (long long)d.slab_layers * d.slab_frames * d.slab_probes;
+        ex.out_stride_probe = 1; ex.out_stride_frame = d.slab_probes;          // in planes
+    }
+    if (mode == 2) {                                                           // dense (frame, probe) images in det_scratch
+        ex.out_stride_probe = img; ex.out_stride_frame = (long long)n_probes * img;
+    }
 
 #ifndef PSB_EMU
     // fused persistent kernels for the steady state (fast_path.cu)
@@ -341,7 +381,7 @@ static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* 
     if (phase) {
         if (!fast) return fail(PSB_ERR_UNSUPPORTED, "psb_propagate_phase: the phase format needs a grid with fused kernels");
         // slice 0 of every frame as t for the generic first pass (one strided launch)
-        TransmitParams tp{phase, f2(t0), (long long)n_frames * img, 1.0f, img, (long long)nz * img};
+        TransmitParams tp{phase, f2(d.t0_scratch), (long long)n_frames * img, 1.0f, img, (long long)nz * img};
         long long blocks = (tp.n + 255) / 256;
         if (blocks > 148 * 16) blocks = 148 * 16;
         int rc0 = go<Transmit>(dim3((unsigned)blocks), 0, s, tp, "transmit");
@@ -350,7 +390,7 @@ static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* 
     }
     int layer = 0;
     for (int z = 0; z < nz; ++z) {
-        row.mul = phase ? f2(t0) : f2(t) + (long long)z * img;
+        row.mul = phase ? f2(d.t0_scratch) : f2(t) + (long long)z * img;
         int rc;
         if (z > 0 && fast) {
 #ifndef PSB_EMU
@@ -360,7 +400,7 @@ static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* 
                 rc = launch_fast_rows(f2(psi_work), n_img, nx, ny, f2(t) + (long long)z * img, (long long)nz * img, n_probes, s);
 #endif
         } else if (z == 0) {
-            row.src = f2(probes); row.src_img_stride = img; row.src_img_mod = n_probes;
+            row.src = f2(d.probes); row.src_img_stride = img; row.src_img_mod = n_probes;
             rc = launch_line_pass(PASS_R1, row, n_img, s);
         } else {
             row.src = f2(psi_work); row.src_img_stride = img; row.src_img_mod = 0;
@@ -368,16 +408,29 @@ static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* 
         }
         if (rc != PSB_OK) return rc;
         const bool last = z == nz - 1;
-        const bool tap = mode == 1 && (last || (layer_every > 0 && (z + 1) % layer_every == 0));
+        const bool tap = mode >= 1 && (last || (layer_every > 0 && (z + 1) % layer_every == 0));
         if (tap) {
-            ex.dst = f2(wf_out) + (long long)layer * stride_layer;
+            if (mode == 2) {
+                ex.dst = f2(d.det_scratch);
+            } else if (slabs) {
+                ex.dst = f2(d.wf_out);
+                ex.slab_plane0 = ((long long)layer * d.slab_frames + d.frame0) * d.slab_probes + d.probe0;
+            } else {
+                ex.dst = f2(d.wf_out) + (long long)layer * d.stride_layer;
+            }
             rc = launch_line_pass(PASS_CX, ex, n_img, s);
             if (rc != PSB_OK) return rc;
+            if (mode == 2) {          // image index = frame*n_probes + probe -> det_out[layer][probe0 + probe][frame0 + frame]
+                rc = sum_pixels_impl(nullptr, f2(d.det_scratch), d.det_mask, n_img, img, img,
+                                     d.det_out + (long long)layer * d.det_stride_layer + (long long)d.probe0 * d.det_stride_probe + d.frame0,
+                                     d.stream, n_probes, d.det_stride_probe, 1);
+                if (rc != PSB_OK) return rc;
+            }
             ++layer;
         }
         if (!last) {
 #ifndef PSB_EMU
-            if (fast) rc = launch_fast_cols(f2(psi_work), n_img, nx, ny, f2(prop_x), f2(prop_y), s);
+            if (fast) rc = launch_fast_cols(f2(psi_work), n_img, nx, ny, f2(d.prop_x), f2(d.prop_y), s);
             else
 #endif
             rc = launch_line_pass(PASS_C, col, n_img, s);
@@ -394,13 +447,30 @@ static int propagate_impl(const psb_c64* probes, const psb_c64* t, const float* 
     return PSB_OK;
 }
 
+static psb_propagate_desc dense_desc(const psb_c64* probes, int n_frames, int n_probes, int nz, int nx, int ny, const psb_c64* prop_x,
+                                     const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out, long long stride_probe,
+                                     long long stride_frame, long long stride_layer, int layer_every, void* stream) {
+    psb_propagate_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.struct_bytes = (int)sizeof(d);
+    d.mode = mode; d.layer_every = layer_every;
+    d.n_frames = n_frames; d.n_probes = n_probes; d.nz = nz; d.nx = nx; d.ny = ny;
+    d.probes = probes; d.prop_x = prop_x; d.prop_y = prop_y; d.psi_work = psi_work; d.wf_out = wf_out;
+    d.stride_probe = stride_probe; d.stride_frame = stride_frame; d.stride_layer = stride_layer;
+    d.stream = stream;
+    return d;
+}
+
 int psb_propagate(const psb_c64* probes, const psb_c64* t, int n_frames, int n_probes, int nz, int nx, int ny,
                   const psb_c64* prop_x, const psb_c64* prop_y, psb_c64* psi_work, int mode, psb_c64* wf_out,
                   long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
                   void* stream) {
     if (!t) return fail(PSB_ERR_INVALID, "psb_propagate: null pointer");
-    return propagate_impl(probes, t, nullptr, nullptr, n_frames, n_probes, nz, nx, ny, prop_x, prop_y, psi_work, mode, wf_out,
-                          stride_probe, stride_frame, stride_layer, layer_every, stream);
+    if (mode != 0 && mode != 1) return fail(PSB_ERR_INVALID, "psb_propagate: mode must be 0 or 1");
+    psb_propagate_desc d = dense_desc(probes, n_frames, n_probes, nz, nx, ny, prop_x, prop_y, psi_work, mode, wf_out, stride_probe,
+                                      stride_frame, stride_layer, layer_every, stream);
+    d.t = t;
+    return psb_propagate_ex(&d);
 }
 
 int psb_propagate_phase(const psb_c64* probes, const float* phase, psb_c64* t0, int n_frames, int n_probes, int nz, int nx,
@@ -408,8 +478,11 @@ int psb_propagate_phase(const psb_c64* probes, const float* phase, psb_c64* t0, 
                         long long stride_probe, long long stride_frame, long long stride_layer, int layer_every,
                         void* stream) {
     if (!phase) return fail(PSB_ERR_INVALID, "psb_propagate_phase: null pointer");
-    return propagate_impl(probes, nullptr, phase, t0, n_frames, n_probes, nz, nx, ny, prop_x, prop_y, psi_work, mode, wf_out,
-                          stride_probe, stride_frame, stride_layer, layer_every, stream);
+    if (mode != 0 && mode != 1) return fail(PSB_ERR_INVALID, "psb_propagate: mode must be 0 or 1");
+    psb_propagate_desc d = dense_desc(probes, n_frames, n_probes, nz, nx, ny, prop_x, prop_y, psi_work, mode, wf_out, stride_probe,
+                                      stride_frame, stride_layer, layer_every, stream);
+    d.phase = phase; d.t0_scratch = t0;
+    return psb_propagate_ex(&d);
 }
 
 int psb_tacaw_intensity(const psb_c64* wf, long long stride_probe, long long stride_frame, int n_probes,
@@ -431,10 +504,11 @@ int psb_tacaw_intensity(const psb_c64* wf, long long stride_probe, long long str
 }
 
 static int sum_pixels_impl(const float* in, const float2* cin, const float* mask, int rows, long long row_stride,
-                           long long npix, double* out, void* stream) {
+                           long long npix, double* out, void* stream, int row_mod, long long out_stride_mod,
+                           long long out_stride_div) {
     if ((!in && !cin) || !out || rows < 0 || npix < 0) return fail(PSB_ERR_INVALID, "psb_sum_pixels: bad argument");
     if (rows == 0) return PSB_OK;
-    SumPixParams p{in, cin, mask, row_stride, npix, out};
+    SumPixParams p{in, cin, mask, row_stride, npix, out, row_mod, out_stride_mod, out_stride_div};
     return go<SumPixels>(dim3(rows), SumPixels::kSmem, as_stream(stream), p, "sum_pixels");
 }
 

@@ -53,6 +53,13 @@ struct PassParams {
     //                      + ((p + n/2) % n)*out_elem_stride + ((line + nlines/2) % nlines)*out_line_stride
     int probes;
     long long out_stride_probe, out_stride_frame, out_elem_stride, out_line_stride;
+    // S_SHIFT, slab layout (slab_world > 1; multi-GPU re-sharding): the shifted element rows sq are split
+    // into slab_world contiguous blocks (the first `slab_rem` blocks hold slab_base + 1 rows, the rest slab_base), and
+    // dst is laid out [block][plane][row in block][line]: block h starts at slab_planes * start_h rows, where a plane
+    // is one (layer, frame, probe) image: plane = slab_plane0 + probe*out_stride_probe + frame*out_stride_frame
+    // (strides in planes).  Every block is then one contiguous message of the all-to-all, no pack pass.
+    int slab_world, slab_base, slab_rem;
+    long long slab_planes, slab_plane0;
     // S_ABS2: real output fout[img*dst_img_stride + ((p + n/2) % n)*out_elem_stride + line*out_line_stride]
     float* fout;
     // S_TRANSMIT2: image = frame*pair_count + ml holds V_{2m} + i*V_{2m+1} with m = pair_begin + ml; t of slice s
@@ -156,16 +163,38 @@ struct LinePass {
         if constexpr (ST == S_SHIFT) {
             const int pr = img % p.probes, fr = img / p.probes;
             const int sl = (line + p.nlines / 2) % p.nlines;
-            float2* dst = p.dst + (long long)pr * p.out_stride_probe + (long long)fr * p.out_stride_frame
-                        + (long long)sl * p.out_line_stride;
             const int half = n / 2;
+            if (p.slab_world > 1) {
+                const long long plane = p.slab_plane0 + (long long)pr * p.out_stride_probe + (long long)fr * p.out_stride_frame;
+                const int big = p.slab_rem * (p.slab_base + 1);          // rows held by the blocks of slab_base + 1 rows
 #pragma unroll
-            for (int e = 0; e < E; ++e) {
-                const int q = j + e * T;
-                if (in_line(q)) {
-                    int sq = q + half;
-                    if (sq >= n) sq -= n;
-                    dst[(long long)sq * p.out_elem_stride] = v[e];
+                for (int e = 0; e < E; ++e) {
+                    const int q = j + e * T;
+                    if (in_line(q)) {
+                        int sq = q + half;
+                        if (sq >= n) sq -= n;
+                        int start, rows;
+                        if (sq < big) {
+                            rows = p.slab_base + 1;
+                            start = (sq / rows) * rows;
+                        } else {
+                            rows = p.slab_base;
+                            start = big + ((sq - big) / rows) * rows;
+                        }
+                        p.dst[(p.slab_planes * start + plane * rows + (sq - start)) * p.out_elem_stride + (long long)sl * p.out_line_stride] = v[e];
+                    }
+                }
+            } else {
+                float2* dst = p.dst + (long long)pr * p.out_stride_probe + (long long)fr * p.out_stride_frame
+                            + (long long)sl * p.out_line_stride;
+#pragma unroll
+                for (int e = 0; e < E; ++e) {
+                    const int q = j + e * T;
+                    if (in_line(q)) {
+                        int sq = q + half;
+                        if (sq >= n) sq -= n;
+                        dst[(long long)sq * p.out_elem_stride] = v[e];
+                    }
                 }
             }
         }

@@ -11,7 +11,9 @@ struct SumPixParams {
     const float* mask;      // optional per-pixel weight
     long long row_stride;   // elements between rows
     long long npix;
-    double* out;            // one value per row
+    double* out;            // one value per row: out[(row % row_mod) * out_stride_mod + (row / row_mod) * out_stride_div]
+    int row_mod;            // 0: out[row]
+    long long out_stride_mod, out_stride_div;
 };
 
 // out[row] = sum_pix in[row, pix] * mask[pix]   -- one CTA per row, float64 accumulation
@@ -41,7 +43,10 @@ struct SumPixels {
             if (t < h) sm[t] += sm[t + h];
             cx.sync();
         }
-        if (t == 0) p.out[row] = sm[0];
+        if (t == 0) {
+            if (p.row_mod > 0) p.out[(row % p.row_mod) * p.out_stride_mod + (row / p.row_mod) * p.out_stride_div] = sm[0];
+            else p.out[row] = sm[0];
+        }
     }
 };
 

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib, hostmath
+from ctypes import sizeof as C_sizeof
 
 # Target size of the wave-function batch that is pushed through all slices at once.  Sized to stay
 # resident in B200's 126 MB L2 across the two passes of a slice step (DESIGN.md "L2 residency"): the
@@ -308,41 +309,75 @@ def layer_count(nz: int, layer_every: int) -> int:
     return len([z for z in range(nz - 1) if (z + 1) % layer_every == 0]) + 1
 
 
+def row_split(n: int, world: int):
+    """kx rows per destination of the frames -> rows all-to-all: (starts, counts), the first n % world blocks one row longer
+    (the rule psb_propagate_ex applies to its slab layout)"""
+    counts = [n // world + (1 if r < n % world else 0) for r in range(world)]
+    starts = [sum(counts[:r]) for r in range(world)]
+    return starts, counts
+
+
 def propagate(plan: SlicePlan, probes: torch.Tensor, t: torch.Tensor, wf_out: Optional[torch.Tensor] = None,
-              frame0: int = 0, probe0: int = 0, layer_every: int = 0, work: Optional[torch.Tensor] = None):
-    """Push `probes` (P, nx, ny) through the transmission stack `t` (F, nz, nx, ny).
+              frame0: int = 0, probe0: int = 0, layer_every: int = 0, work: Optional[torch.Tensor] = None,
+              slabs=None, detector=None):
+    """Push `probes` (P, nx, ny) through the transmission stack `t` (F, nz, nx, ny; complex64 t or float32 phases).
 
     wf_out is None: returns the real-space exit waves (F, P, nx, ny)  (the reference's Propagate()).
     wf_out (L, Ptot, Ttot, nx, ny): writes fftshift(fft2(exit)) for frames [frame0, frame0+F) and probes
-    [probe0, probe0+P) of every layer (the reference's per-frame worker + copy loop)."""
+    [probe0, probe0+P) of every layer (the reference's per-frame worker + copy loop).
+    slabs=(world, L, Ttot, Ptot) with a flat wf_out of L*Ptot*Ttot*nx*ny elements: the same values in the per-destination
+    slab layout of psb_propagate_ex (multi-GPU runs: each slab is one message of the frames -> kx-rows all-to-all).
+    detector=(mask (nx, ny) float32 in shifted k order, out (L, Ptot, Ttot) float64, scratch (F*P, nx, ny) complex64):
+    only sum_k |psi_k| * mask per (layer, probe, frame) is kept (HAADF without the exit-wave cube)."""
     F = t.shape[0]
     P = probes.shape[0]
     nx, ny, nz = plan.nx, plan.ny, plan.nz
     if work is None:
         work = torch.empty((F * P, nx, ny), dtype=torch.complex64, device=plan.device)
     L = _lib.lib()
-    st = _stream(plan.device)
+    d = _lib.PropagateDesc()
+    d.struct_bytes = C_sizeof(d)
+    d.layer_every = layer_every
+    d.n_frames, d.n_probes, d.nz, d.nx, d.ny = F, P, nz, nx, ny
+    d.probes = probes.data_ptr()
+    d.prop_x, d.prop_y = plan.prop_x.data_ptr(), plan.prop_y.data_ptr()
+    d.psi_work = work.data_ptr()
+    d.stream = _stream(plan.device)
     if t.dtype == torch.float32:                 # phase stack (build_transmission(phase=True))
         t0 = torch.empty((F, nx, ny), dtype=torch.complex64, device=plan.device)
-
-        def call(mode, base, sp, sf, sl, le):
-            return L.psb_propagate_phase(probes.data_ptr(), t.data_ptr(), t0.data_ptr(), F, P, nz, nx, ny,
-                                         plan.prop_x.data_ptr(), plan.prop_y.data_ptr(), work.data_ptr(), mode, base, sp, sf, sl,
-                                         le, st)
+        d.phase, d.t0_scratch = t.data_ptr(), t0.data_ptr()
     else:
-        def call(mode, base, sp, sf, sl, le):
-            return L.psb_propagate(probes.data_ptr(), t.data_ptr(), F, P, nz, nx, ny, plan.prop_x.data_ptr(),
-                                   plan.prop_y.data_ptr(), work.data_ptr(), mode, base, sp, sf, sl, le, st)
-    if wf_out is None:
-        with _on(plan.device):
-            _lib.check(call(0, None, 0, 0, 0, 0), "psb_propagate")
-        return work.view(F, P, nx, ny)
-    Lr, Pt, Tt = wf_out.shape[:3]
-    assert wf_out.is_contiguous() and Lr == layer_count(nz, layer_every)
+        d.t = t.data_ptr()
     img = nx * ny
-    base = wf_out.data_ptr() + 8 * (probe0 * Tt * img + frame0 * img)
+    if detector is not None:
+        mask, out, scratch = detector
+        assert mask.dtype == torch.float32 and mask.is_contiguous() and out.dtype == torch.float64 and out.is_contiguous()
+        assert scratch.numel() >= F * P * img and out.shape[0] == layer_count(nz, layer_every)
+        d.mode = 2
+        d.det_mask, d.det_out, d.det_scratch = mask.data_ptr(), out.data_ptr(), scratch.data_ptr()
+        d.det_stride_layer, d.det_stride_probe = out.stride(0), out.stride(1)
+        d.frame0, d.probe0 = frame0, probe0
+    elif wf_out is None:
+        d.mode = 0
+    elif slabs is not None:
+        world, Lr, Tt, Pt = slabs
+        assert wf_out.is_contiguous() and wf_out.numel() == Lr * Pt * Tt * img and Lr == layer_count(nz, layer_every)
+        d.mode = 1
+        d.wf_out = wf_out.data_ptr()
+        d.slab_world, d.slab_layers, d.slab_frames, d.slab_probes = world, Lr, Tt, Pt
+        d.frame0, d.probe0 = frame0, probe0
+    else:
+        Lr, Pt, Tt = wf_out.shape[:3]
+        assert wf_out.is_contiguous() and Lr == layer_count(nz, layer_every)
+        d.mode = 1
+        d.wf_out = wf_out.data_ptr() + 8 * (probe0 * Tt * img + frame0 * img)
+        d.stride_probe, d.stride_frame, d.stride_layer = Tt * img, img, Pt * Tt * img
     with _on(plan.device):
-        _lib.check(call(1, base, Tt * img, img, Pt * Tt * img, layer_every), "psb_propagate")
+        _lib.check(L.psb_propagate_ex(d), "psb_propagate")
+    if detector is not None:
+        return detector[1]
+    if wf_out is None:
+        return work.view(F, P, nx, ny)
     return wf_out
 
 

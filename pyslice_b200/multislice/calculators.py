@@ -27,7 +27,7 @@ import numpy as np
 import torch
 
 from .. import engine, hostmath
-from ..postprocessing.wf_data import WFData
+from ..postprocessing.wf_data import SlabStore, WFData
 from .multislice import Probe, create_batched_probes
 from .potentials import gridFromTrajectory
 from .trajectory import Trajectory
@@ -135,6 +135,7 @@ class MultisliceCalculator:
         shard_frames: Optional[bool] = None,
         frame_cache=False,
         cache_key: str = "positions",
+        adf_collection_angle: Optional[float] = None,
     ):
         """Same keyword arguments and defaults as the reference (calculators.py:96-109).
         `defocus`, `batch_size`, `save_path`, `cleanup_temp_files` are accepted and, as in the
@@ -144,7 +145,12 @@ class MultisliceCalculator:
         frame's exit waves are written to `<dir>/torch_<key>/frame_<i>.npy` in the reference's wire format
         ((P, nx, ny, 1, 1) complex128, calculators.py:276,311) by a writer thread, and frames whose file exists
         are loaded instead of computed (calculators.py:259-260).  cache_key: "positions" (default: the reference's
-        parameters plus a digest of the positions) or "reference" (exactly calculators.py:81-92)."""
+        parameters plus a digest of the positions) or "reference" (exactly calculators.py:81-92).
+
+        adf_collection_angle (mrad): imaging runs that only want `HAADFData(wf).calculateADF(angle)`.  run() then keeps
+        the detector sums sum_k |psi_k| * (|k| > angle/lambda) per (layer, probe, frame) -- the reduction of reference
+        haadf_data.py:43-65, taken right after each exit FFT -- and never allocates the (P, T, nx, ny) exit-wave cube
+        (54 GB at config C3); `wavefunction_data` is None on such a WFData."""
         if slice_axis != 2:
             raise NotImplementedError("pyslice_b200 supports slice_axis=2 only")
         self.trajectory = trajectory
@@ -158,6 +164,9 @@ class MultisliceCalculator:
         self.cleanup_temp_files = cleanup_temp_files
         self.slice_axis = slice_axis
         self.layer_every = int(layer_every)
+        self.adf_collection_angle = adf_collection_angle
+        if adf_collection_angle is not None and frame_cache:
+            raise ValueError("adf_collection_angle keeps no exit waves: not available with the frame cache")
         if cache_key not in ("positions", "reference"):
             raise ValueError("cache_key must be 'positions' or 'reference'")
         if frame_cache and self.layer_every > 0:
@@ -242,7 +251,25 @@ class MultisliceCalculator:
         # the result store is allocated AFTER the multi-GB stack: while a previous result is still alive the caching
         # allocator would otherwise carve the new store out of the cached stack block and then cudaMalloc a fresh stack
         # (tens of milliseconds of idle GPU, seen as random gaps between the phases of repeated runs)
-        store = torch.empty((self.n_layers, P, T_loc, nx, ny), dtype=torch.complex64, device=self.device)
+        # Result store.  One process: (L, P, T, nx, ny), exposed as the reference's (P, T, nx, ny, L).  Frame-sharded run:
+        # the per-destination slab layout of the frames -> kx-rows all-to-all (SlabStore), written by the exit FFT itself.
+        # Detector-only run: (L, P, T) float64 sums and one batch of k-space scratch.
+        world = self.shard.world if self.shard is not None else 1
+        slabs = world > 1 and self.output_dir is None and self.adf_collection_angle is None
+        det = None
+        if self.adf_collection_angle is not None:
+            kxs32 = torch.fft.fftshift(torch.fft.fftfreq(nx, self.sampling))
+            kys32 = torch.fft.fftshift(torch.fft.fftfreq(ny, self.sampling))
+            q = torch.sqrt(kxs32[:, None] ** 2 + kys32[None, :] ** 2)
+            radius = (self.adf_collection_angle * 1e-3) / self.base_probe.wavelength
+            mask = (q > radius).to(torch.float32).to(self.device).contiguous()       # haadf_data.py:52-57
+            sums = torch.zeros((self.n_layers, P, max(T_loc, 1)), dtype=torch.float64, device=self.device)
+            det = (mask, sums, torch.empty((fb * min(pb, P), nx, ny), dtype=torch.complex64, device=self.device))
+            store = None
+        elif slabs:
+            store = torch.empty((self.n_layers * P * T_loc * nx * ny,), dtype=torch.complex64, device=self.device)
+        else:
+            store = torch.empty((self.n_layers, P, T_loc, nx, ny), dtype=torch.complex64, device=self.device)
         positions = self.trajectory.positions
         # frame cache (opt-in): cached frames are loaded, the others are computed in contiguous runs and handed to
         # a writer thread (D2H on a side stream would buy nothing here: the files are written by the host anyway)
@@ -304,7 +331,8 @@ class MultisliceCalculator:
                 for p0 in range(0, P, pb):
                     np_ = min(pb, P - p0)
                     engine.propagate(plan, self._probes[p0:p0 + np_], t, wf_out=store, frame0=b0, probe0=p0,
-                                     layer_every=self.layer_every, work=work)
+                                     layer_every=self.layer_every, work=work, detector=det,
+                                     slabs=(world, self.n_layers, T_loc, P) if slabs else None)
             if writer is not None:
                 host = store[0, :, b0:b0 + nb].to("cpu")                 # (P, nb, nx, ny); synchronises this batch
                 for k in range(nb):
@@ -318,8 +346,13 @@ class MultisliceCalculator:
                     self.output_dir.rmdir()
                 except OSError:
                     pass
-        # (L, P, T, nx, ny) storage exposed in the reference's (P, T, nx, ny, L) index order
-        self.wavefunction_data = store.permute(1, 2, 3, 4, 0)
+        if det is not None:
+            self.wavefunction_data = None
+        elif slabs:
+            self.wavefunction_data = SlabStore(store, world, self.n_layers, T_loc, P, nx, ny)
+        else:
+            # (L, P, T, nx, ny) storage exposed in the reference's (P, T, nx, ny, L) index order
+            self.wavefunction_data = store.permute(1, 2, 3, 4, 0)
         logger.info(f"Simulation completed in {time.time() - t_start:.2f}s ({T_loc} frames computed)")
 
         # axis labels exactly as the reference builds them (calculators.py:218-221): float32, from
@@ -335,4 +368,7 @@ class MultisliceCalculator:
         wf = WFData(probe_positions=self.probe_positions, time=time_array, kxs=kxs, kys=kys, layer=layer_array,
                     wavefunction_data=self.wavefunction_data, probe=self.base_probe)
         wf.shard = self.shard
+        if det is not None:
+            wf.adf_sums = det[1][:, :, :T_loc]          # (L, P, T_local) float64 on the device
+            wf.adf_collection_angle = self.adf_collection_angle
         return wf

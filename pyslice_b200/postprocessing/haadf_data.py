@@ -31,21 +31,40 @@ class HAADFData(WFData):
         radius = (collection_angle * 1e-3) / self.probe.wavelength
         mask = torch.zeros(q.shape)
         mask[q > radius] = 1
-        wf = self.wavefunction_data[:, :, :, :, -1]
-        if not hasattr(wf, "dim"):
-            wf = torch.from_numpy(np.asarray(wf))
-        dev = engine._device(wf.device if wf.device.type == "cuda" else None)
-        wf = wf.to(device=dev, dtype=torch.complex64).contiguous()
-        P, T, nx, ny = wf.shape
-        sums = engine.sum_pixels(wf.reshape(P * T, nx * ny), mask.to(dev, torch.float32).reshape(-1))
+        from .wf_data import SlabStore
         shard = getattr(self, "shard", None)
+        sums_dev = getattr(self, "adf_sums", None)
+        if sums_dev is not None:
+            # detector-only run (MultisliceCalculator.setup(adf_collection_angle=...)): the sums were taken after each exit FFT
+            if abs(float(self.adf_collection_angle) - float(collection_angle)) > 1e-12:
+                raise ValueError(f"this WFData holds detector sums for a collection angle of {self.adf_collection_angle} mrad only")
+            sums = sums_dev[-1]                                                  # exit layer, (P, T_local)
+            P, T = sums.shape
+        elif isinstance(self.wavefunction_data, SlabStore):
+            store = self.wavefunction_data
+            dev = store.device
+            P, T = store.P, store.T
+            sums = torch.zeros((T * P,), dtype=torch.float64, device=dev)
+            for h in range(store.world):                                         # detector rows of every block
+                blk = store.block(h, store.L - 1)                                # (T, P, rows_h, ny)
+                m = mask[store.row_starts[h]:store.row_starts[h] + store.row_counts[h]].to(dev, torch.float32).reshape(-1)
+                sums += engine.sum_pixels(blk.reshape(T * P, -1), m.contiguous())
+            sums = sums.reshape(T, P).t()
+        else:
+            wf = self.wavefunction_data[:, :, :, :, -1]
+            if not hasattr(wf, "dim"):
+                wf = torch.from_numpy(np.asarray(wf))
+            dev = engine._device(wf.device if wf.device.type == "cuda" else None)
+            wf = wf.to(device=dev, dtype=torch.complex64).contiguous()
+            P, T, nx, ny = wf.shape
+            sums = engine.sum_pixels(wf.reshape(P * T, nx * ny), mask.to(dev, torch.float32).reshape(-1)).reshape(P, T)
         if shard is not None and shard.world > 1:
             import torch.distributed as dist
-            tot = sums.reshape(P, T).sum(dim=1)
+            tot = sums.sum(dim=1)
             dist.all_reduce(tot)
             per_probe = (tot / float(shard.total)).cpu()
         else:
-            per_probe = sums.reshape(P, T).mean(dim=1).cpu()
+            per_probe = sums.mean(dim=1).cpu()
         self.adf = torch.zeros((len(self.xs), len(self.ys)))
         for i, x in enumerate(self.xs.tolist()):
             for j, y in enumerate(self.ys.tolist()):

@@ -20,18 +20,60 @@ logger = logging.getLogger(__name__)
 
 
 def _row_split(n: int, world: int):
-    counts = [n // world + (1 if r < n % world else 0) for r in range(world)]
-    starts = [sum(counts[:r]) for r in range(world)]
+    starts, counts = engine.row_split(n, world)
     return starts, counts
 
 
-def frames_to_rows_all_to_all(wf_layer: torch.Tensor, shard, group=None) -> torch.Tensor:
-    """(P, T_local, nx, ny) frame shard -> (P, T_total, nx_local, ny) kx-row shard.
-
-    The one collective of the pipeline: rank g sends rank h the slab
-    psi[:, F_g, K_h, :].  Returned tensor is a (P, T, rows, ny) view of a (T, P, rows, ny) buffer so
-    every source's block is contiguous for the exchange."""
+def _exchange(send, recv, rank, group=None):
+    """one all-to-all of contiguous blocks: send[h] -> rank h, recv[g] <- rank g (views, nothing is packed)"""
     import torch.distributed as dist
+    send_r = [torch.view_as_real(x) for x in send]
+    recv_r = [torch.view_as_real(x) for x in recv]
+    if dist.get_backend(group) == "nccl":
+        dist.all_to_all(recv_r, send_r, group=group)          # grouped send/recv over NVLink 5 / NVSwitch
+        return
+    # gloo (CPU tests of the host logic) has no all_to_all: pairwise exchange
+    reqs = []
+    for h in range(len(send)):
+        if h == rank:
+            recv_r[h].copy_(send_r[h])
+            continue
+        reqs.append(dist.isend(send_r[h], h, group=group))
+        reqs.append(dist.irecv(recv_r[h], h, group=group))
+    for r in reqs:
+        r.wait()
+
+
+def slabs_to_rows_all_to_all(store, layer: int, shard, group=None) -> torch.Tensor:
+    """SlabStore (frame shard, slab layout) -> (P, T_total, nx_local, ny) kx-row shard of one layer.
+
+    The one collective of the pipeline: rank g sends rank h the slab psi[:, F_g, K_h, :], which the exit
+    FFT already wrote as one contiguous block per (destination, layer).  With a single layer the send side is the whole
+    store and the exchange is one `all_to_all_single`; with several layers the blocks of the requested layer are sent as
+    views.  The result is a (P, T, rows, ny) view of a (T, P, rows, ny) buffer (every source's frames contiguous)."""
+    import torch.distributed as dist
+    world, rank = shard.world, shard.rank
+    P, ny = store.P, store.ny
+    rows = store.row_counts[rank]
+    full = torch.empty((shard.total, P, rows, ny), dtype=store.dtype, device=store.device)
+    if store.L == 1 and dist.get_backend(group) == "nccl":
+        in_split = [2 * store.T * P * store.row_counts[h] * ny for h in range(world)]
+        out_split = [2 * shard.counts[g] * P * rows * ny for g in range(world)]
+        dist.all_to_all_single(torch.view_as_real(full).reshape(-1), torch.view_as_real(store.buf).reshape(-1),
+                               output_split_sizes=out_split, input_split_sizes=in_split, group=group)
+        return full.permute(1, 0, 2, 3)
+    send = [store.block(h, layer) for h in range(world)]                       # (T_loc, P, rows_h, ny) contiguous views
+    recv, t0 = [], 0
+    for g in range(world):
+        recv.append(full[t0:t0 + shard.counts[g]])
+        t0 += shard.counts[g]
+    _exchange(send, recv, rank, group)
+    return full.permute(1, 0, 2, 3)
+
+
+def frames_to_rows_all_to_all(wf_layer: torch.Tensor, shard, group=None) -> torch.Tensor:
+    """(P, T_local, nx, ny) dense frame shard -> (P, T_total, nx_local, ny) kx-row shard (packs one block per destination;
+    used when the exit waves are not in the slab layout: frame-cache runs, WFData assembled by hand)."""
     P, T_loc, nx, ny = wf_layer.shape
     world, rank = shard.world, shard.rank
     starts, counts = _row_split(nx, world)
@@ -43,21 +85,7 @@ def frames_to_rows_all_to_all(wf_layer: torch.Tensor, shard, group=None) -> torc
     for g in range(world):
         recv.append(full[t0:t0 + shard.counts[g]])
         t0 += shard.counts[g]
-    send_r = [torch.view_as_real(x) for x in send]
-    recv_r = [torch.view_as_real(x) for x in recv]
-    if dist.get_backend(group) == "nccl":
-        dist.all_to_all(recv_r, send_r, group=group)          # NVLink 5 / NVSwitch
-    else:
-        # gloo (CPU tests of the host logic) has no all_to_all: pairwise exchange
-        reqs = []
-        for h in range(world):
-            if h == rank:
-                recv_r[h].copy_(send_r[h])
-                continue
-            reqs.append(dist.isend(send_r[h], h, group=group))
-            reqs.append(dist.irecv(recv_r[h], h, group=group))
-        for r in reqs:
-            r.wait()
+    _exchange(send, recv, rank, group)
     return full.permute(1, 0, 2, 3)
 
 
@@ -81,6 +109,17 @@ class TACAWData(WFData):
         dt = self.time[1] - self.time[0]
         self.frequencies = np.fft.fftshift(np.fft.fftfreq(n_freq, d=dt))
 
+        from .wf_data import SlabStore
+        shard = getattr(self, "shard", None)
+        timer = getattr(self, "_timer", None) or engine.NO_TIMER      # bench.py: CUDA-event phases
+        if isinstance(self.wavefunction_data, SlabStore):              # frame-sharded run: blocks are ready to send
+            store = self.wavefunction_data
+            self.row_range = (store.row_starts[shard.rank], store.row_starts[shard.rank] + store.row_counts[shard.rank])
+            with timer.phase("all_to_all"):
+                wf_layer = slabs_to_rows_all_to_all(store, layer_index, shard)
+            with timer.phase("tacaw"):
+                self.intensity = engine.tacaw_intensity(wf_layer)
+            return
         wf_layer = self.wavefunction_data[:, :, :, :, layer_index]
         if not hasattr(wf_layer, "dim"):
             wf_layer = torch.from_numpy(np.asarray(wf_layer))
@@ -88,8 +127,6 @@ class TACAWData(WFData):
         wf_layer = wf_layer.to(device=dev, dtype=torch.complex64)
         if wf_layer.stride(3) != 1 or wf_layer.stride(2) != wf_layer.shape[3]:
             wf_layer = wf_layer.contiguous()
-        shard = getattr(self, "shard", None)
-        timer = getattr(self, "_timer", None) or engine.NO_TIMER      # bench.py: CUDA-event phases
         self.row_range = (0, wf_layer.shape[2])
         if shard is not None and shard.world > 1:
             starts, counts = _row_split(wf_layer.shape[2], shard.world)

@@ -54,6 +54,32 @@ def _worker(rank, world, port, n_frames, ret):
         np.testing.assert_allclose(tac.dispersion(kx, ky), tac1.dispersion(kx, ky), rtol=0, atol=0)
         mask = (np.arange(32)[:, None] + np.arange(24)[None, :]) % 3 == 0
         np.testing.assert_allclose(tac.masked_spectrum(mask), tac1.masked_spectrum(mask), rtol=1e-12)
+        # several probes + layer taps on a grid whose kx rows do not split evenly (23 rows over 2 ranks): multi-layer slab
+        # store, the layer-wise exchange, HAADF over the blocks, and the detector-only run that keeps no exit waves
+        from pyslice_b200.postprocessing.haadf_data import HAADFData
+        traj2 = synthetic.random_trajectory(n_atoms=40, box=(2.25, 1.55, 1.2), n_frames=3, seed=4, types=(6, 14))
+        pp = [(0.5, 0.4), (1.5, 1.0)]
+        kw = dict(aperture=30.0, voltage_eV=100e3, probe_positions=pp, layer_every=2)
+        calc2 = MultisliceCalculator()
+        calc2.setup(traj2, **kw)
+        wf2 = calc2.run()
+        single2 = MultisliceCalculator()
+        single2.setup(traj2, shard_frames=False, **kw)
+        wf2s = single2.run()
+        assert wf2.wavefunction_data.shape == (2, calc2.shard.counts[rank], 23, 16, 2)
+        f0 = calc2.shard.start
+        assert torch.equal(wf2.wavefunction_data.dense(), wf2s.wavefunction_data[:, f0:f0 + calc2.shard.counts[rank]])
+        for layer in (0, 1):
+            ta, tb = TACAWData(wf2, layer_index=layer), TACAWData(wf2s, layer_index=layer)
+            r0, r1 = ta.row_range
+            assert torch.equal(ta.intensity, tb.intensity[:, :, r0:r1])
+        adf, adf1 = HAADFData(wf2).calculateADF(20.0), HAADFData(wf2s).calculateADF(20.0)
+        np.testing.assert_allclose(adf.numpy(), adf1.numpy(), rtol=1e-6)
+        calc3 = MultisliceCalculator()
+        calc3.setup(traj2, adf_collection_angle=20.0, **kw)
+        wf3 = calc3.run()
+        assert wf3.wavefunction_data is None and wf3.adf_sums.shape == (2, 2, calc3.shard.counts[rank])
+        np.testing.assert_allclose(HAADFData(wf3).calculateADF(20.0).numpy(), adf1.numpy(), rtol=1e-6)
         ret[rank] = "ok"
     except Exception as e:  # pragma: no cover
         import traceback

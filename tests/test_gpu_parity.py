@@ -107,6 +107,14 @@ def test_small64_runs_against_reference_golden():
             assert rel_l2(wf2.wavefunction_data[p, f, :, :, 0].cpu().numpy(), g["wf_probes"][p, f, :, :, 0]) < 1e-4
     adf = HAADFData(wf2).calculateADF(45)
     assert rel_l2(adf.numpy(), g["adf"]) < 1e-4
+    # detector-only run: the same image without ever allocating the exit-wave cube (sums taken after each exit FFT)
+    calc.setup(traj, aperture=30.0, voltage_eV=100e3, probe_positions=g["probe_xy"], adf_collection_angle=45)
+    wf3 = calc.run()
+    assert wf3.wavefunction_data is None and tuple(wf3.adf_sums.shape) == (1, 4, 3)
+    adf3 = HAADFData(wf3).calculateADF(45)
+    assert rel_l2(adf3.numpy(), g["adf"]) < 1e-4 and rel_l2(adf3.numpy(), adf.numpy()) < 1e-6
+    with pytest.raises(ValueError):
+        HAADFData(wf3).calculateADF(30)
 
 
 def test_tacaw48_against_reference_golden():
