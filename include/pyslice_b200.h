@@ -45,6 +45,10 @@ long long psb_launch_count(void);
 /* diagnostic switch between kernel generations (all CUDA; used by microbenchmarks and A/B parity tests):
  * 0 = generic line-pass kernels, anything else = fused persistent kernels (default). */
 void psb_set_fast_path(int level);
+/* CUDA-graph replay of repeated launch sequences (default on; environment PSB_GRAPHS=0 or psb_set_graph_mode(0) turn it off):
+ * psb_propagate_ex / psb_propagate / psb_propagate_phase and psb_build_transmission / psb_build_phase called again with the
+ * same buffers and sizes replay the ~1000 launches of a batch as one graph launch.  Results are identical either way. */
+void psb_set_graph_mode(int on);
 
 /* ---- atom -> slice binning: src/multislice/potentials.py:297-317 (+ bounds :304-305) -------------
  * positions (F, A, 3) float64; type_idx (A) dense type index in [0, ntypes);

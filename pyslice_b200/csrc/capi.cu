@@ -2,6 +2,7 @@
 #include "../../include/pyslice_b200.h"
 
 #include "fast_path.h"
+#include "graph_cache.h"
 #include "tacaw_fast.h"
 #include "line_pass.cuh"
 #include "potential_kernels.cuh"
@@ -60,6 +61,9 @@ int psb_version(void) { return 100; }
 const char* psb_last_error(void) { return last_error(); }
 int psb_sm_count(void) { return rt::sm_count(); }
 void psb_release_tables(void) {
+#ifndef PSB_EMU
+    graph_cache_release();        // cached graphs hold pointers into the tables freed below
+#endif
     free_all_tables();
 #ifndef PSB_EMU
     sf_fast_release();
@@ -67,6 +71,13 @@ void psb_release_tables(void) {
 #endif
 }
 long long psb_launch_count(void) { return launch_counter(); }
+void psb_set_graph_mode(int on) {
+#ifndef PSB_EMU
+    graph_mode_set(on);
+#else
+    (void)on;
+#endif
+}
 void psb_set_fast_path(int level) {
 #ifndef PSB_EMU
     fast_path_enable(level);
@@ -113,10 +124,12 @@ int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames
 }
 
 // phase_out != nullptr: the stack is written as float32 phases sigma*V instead of t = exp(i*sigma*V) (fused grids only)
-static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
-                      int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
-                      float scale, float sigma, psb_c64* t_out, float* v_out, float* phase_out, psb_c64* scratch,
-                      long long scratch_elems, void* stream) {
+// `s` is the stream the launches go to (the caller's, or the capture stream while a graph is recorded); `owner` is always
+// the caller's stream: the pipelined structure factor keeps its workspace per (device, caller stream)
+static int build_eager(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
+                       int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
+                       float scale, float sigma, psb_c64* t_out, float* v_out, float* phase_out, psb_c64* scratch,
+                       long long scratch_elems, cudaStream_t s, cudaStream_t owner) {
     if (!offsets || !ux || !uy || !formfactors || (!t_out && !phase_out) || !scratch)
         return fail(PSB_ERR_INVALID, "psb_build_transmission: null pointer");
 #ifndef PSB_EMU
@@ -127,7 +140,6 @@ static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t
         return fail(PSB_ERR_UNSUPPORTED, "psb_build_phase: the phase format needs a grid with fused kernels (256 / 512 points)");
     if (n_frames < 0 || nz < 1 || nx < 1 || ny < 1 || ntypes < 1) return fail(PSB_ERR_INVALID, "psb_build_transmission: bad sizes");
     if (n_frames == 0) return PSB_OK;
-    cudaStream_t s = as_stream(stream);
     const long long img = (long long)nx * ny;
     const int npairs = (nz + 1) / 2;
     // Work in chunks of slice-pair images small enough to stay in L2 between the three kernels
@@ -151,7 +163,7 @@ static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t
     // pipelined structure factor (sf_fast.cu) unless the type count exceeds what it stages: then the generic kernel
     const bool sf_fast = fast_path_enabled() && sf_fast_supported(ntypes);
     if (sf_fast) {
-        int rc0 = sf_fast_prepare(formfactors, ntypes, nx, ny, s);
+        int rc0 = sf_fast_prepare(formfactors, ntypes, nx, ny, s, owner);
         if (rc0 != PSB_OK) return rc0;
     }
 #endif
@@ -186,7 +198,7 @@ static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t
             int rc;
 #ifndef PSB_EMU
             if (sf_fast)
-                rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, f2(scratch), s);
+                rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, f2(scratch), s, owner);
             else
 #endif
             rc = go<StructureFactorPaired>(dim3(tiles, (unsigned)groups, nf), StructureFactorPaired::kSmem, s, sp, "structure_factor");
@@ -217,6 +229,35 @@ static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t
         }
     }
     return PSB_OK;
+}
+
+static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
+                      int n_atoms, int nz, int ntypes, int nx, int ny, const float* formfactors,
+                      float scale, float sigma, psb_c64* t_out, float* v_out, float* phase_out, psb_c64* scratch,
+                      long long scratch_elems, void* stream) {
+    cudaStream_t owner = as_stream(stream);
+    auto eager = [&](cudaStream_t s) {
+        return build_eager(offsets, ux, uy, n_frames, n_atoms, nz, ntypes, nx, ny, formfactors, scale, sigma, t_out, v_out,
+                           phase_out, scratch, scratch_elems, s, owner);
+    };
+#ifndef PSB_EMU
+    // same buffers and sizes as an earlier call on this stream -> the recorded launch sequence is replayed as one graph
+    struct Key {
+        const void *offsets, *ux, *uy, *ff, *t_out, *v_out, *phase_out, *scratch, *owner;
+        long long scratch_elems;
+        int n_frames, n_atoms, nz, ntypes, nx, ny, level, tag;
+        float scale, sigma;
+    } key;
+    std::memset(&key, 0, sizeof(key));
+    key.offsets = offsets; key.ux = ux; key.uy = uy; key.ff = formfactors; key.t_out = t_out; key.v_out = v_out;
+    key.phase_out = phase_out; key.scratch = scratch; key.owner = owner; key.scratch_elems = scratch_elems;
+    key.n_frames = n_frames; key.n_atoms = n_atoms; key.nz = nz; key.ntypes = ntypes; key.nx = nx; key.ny = ny;
+    key.level = fast_path_level(); key.tag = 0x6275696c;
+    key.scale = scale; key.sigma = sigma;
+    return run_graphed(&key, sizeof(key), owner, eager);
+#else
+    return eager(owner);
+#endif
 }
 
 int psb_build_transmission(const int32_t* offsets, const uint32_t* ux, const uint32_t* uy, int n_frames,
@@ -299,50 +340,14 @@ static int sum_pixels_impl(const float* in, const float2* cin, const float* mask
                            long long npix, double* out, void* stream, int row_mod = 0, long long out_stride_mod = 0,
                            long long out_stride_div = 0);
 
-// desc.phase != nullptr: the stack holds float32 phases; t0_scratch (n_frames, nx, ny) receives exp(i*phase) of slice 0 for
-// the generic first pass, every later slice is evaluated inside the fused row pass
-int psb_propagate_ex(const psb_propagate_desc* dp) {
-    if (!dp || dp->struct_bytes != (int)sizeof(psb_propagate_desc))
-        return fail(PSB_ERR_INVALID, "psb_propagate_ex: descriptor size mismatch (header / library version skew)");
-    const psb_propagate_desc& d = *dp;
+// the launch sequence of one psb_propagate_ex call (arguments already validated), issued on stream `s`
+static int propagate_eager(const psb_propagate_desc& d, cudaStream_t s) {
     const psb_c64* t = d.t;
     const float* phase = d.phase;
     const int n_frames = d.n_frames, n_probes = d.n_probes, nz = d.nz, nx = d.nx, ny = d.ny, mode = d.mode;
-    if (!d.probes || (!t && !phase) || (t && phase) || !d.prop_x || !d.prop_y || !d.psi_work)
-        return fail(PSB_ERR_INVALID, "psb_propagate: null pointer (or both t and phase given)");
-    if (phase && !d.t0_scratch) return fail(PSB_ERR_INVALID, "psb_propagate_phase: t0 scratch required");
-    if (mode < 0 || mode > 2) return fail(PSB_ERR_INVALID, "psb_propagate: mode must be 0, 1 or 2");
-    if (mode == 1 && !d.wf_out) return fail(PSB_ERR_INVALID, "psb_propagate: wf_out required in mode 1");
-    if (mode == 2 && (!d.det_mask || !d.det_out || !d.det_scratch))
-        return fail(PSB_ERR_INVALID, "psb_propagate: det_mask, det_out and det_scratch required in mode 2");
-    if (n_frames < 0 || n_probes < 1 || nz < 1 || nx < 1 || ny < 1 || d.layer_every < 0)
-        return fail(PSB_ERR_INVALID, "psb_propagate: bad sizes");
     const bool slabs = mode == 1 && d.slab_world > 1;
-    if (slabs && (d.slab_world > nx || d.slab_layers < 1 || d.slab_frames < 1 || d.slab_probes < 1 || d.frame0 < 0 || d.probe0 < 0 ||
-                  d.frame0 + n_frames > d.slab_frames || d.probe0 + n_probes > d.slab_probes))
-        return fail(PSB_ERR_INVALID, "psb_propagate: bad slab layout");
-    const long long n_img_ll = (long long)n_frames * n_probes;
-    if (n_img_ll == 0) return PSB_OK;
-    cudaStream_t s = as_stream(d.stream);
     const long long img = (long long)nx * ny;
-    // the generic passes put the image index in gridDim.y: larger batches go through in slices of whole frames
-    if (n_img_ll > 65535) {
-        const int fmax = 65535 / n_probes;
-        if (fmax < 1) return fail(PSB_ERR_UNSUPPORTED, "psb_propagate: more than 65535 probes per call");
-        for (int f0 = 0; f0 < n_frames; f0 += fmax) {
-            psb_propagate_desc part = d;
-            part.n_frames = n_frames - f0 < fmax ? n_frames - f0 : fmax;
-            if (t) part.t = t + (long long)f0 * nz * img;
-            if (phase) part.phase = phase + (long long)f0 * nz * img;
-            if (mode == 1 && !slabs) part.wf_out = d.wf_out + (long long)f0 * d.stride_frame;
-            part.psi_work = d.psi_work + (long long)f0 * n_probes * img;          // mode 0 leaves its result there
-            part.frame0 = d.frame0 + f0;
-            int rc = psb_propagate_ex(&part);
-            if (rc != PSB_OK) return rc;
-        }
-        return PSB_OK;
-    }
-    const int n_img = (int)n_img_ll;
+    const int n_img = n_frames * n_probes;
     const int layer_every = d.layer_every;
     psb_c64* psi_work = d.psi_work;
 
@@ -423,7 +428,7 @@ int psb_propagate_ex(const psb_propagate_desc* dp) {
             if (mode == 2) {          // image index = frame*n_probes + probe -> det_out[layer][probe0 + probe][frame0 + frame]
                 rc = sum_pixels_impl(nullptr, f2(d.det_scratch), d.det_mask, n_img, img, img,
                                      d.det_out + (long long)layer * d.det_stride_layer + (long long)d.probe0 * d.det_stride_probe + d.frame0,
-                                     d.stream, n_probes, d.det_stride_probe, 1);
+                                     (void*)s, n_probes, d.det_stride_probe, 1);
                 if (rc != PSB_OK) return rc;
             }
             ++layer;
@@ -445,6 +450,66 @@ int psb_propagate_ex(const psb_propagate_desc* dp) {
         return launch_line_pass(PASS_INV_ROWS, inv, n_img, s);
     }
     return PSB_OK;
+}
+
+// desc.phase != nullptr: the stack holds float32 phases; t0_scratch (n_frames, nx, ny) receives exp(i*phase) of slice 0 for
+// the generic first pass, every later slice is evaluated inside the fused row pass
+int psb_propagate_ex(const psb_propagate_desc* dp) {
+    if (!dp || dp->struct_bytes != (int)sizeof(psb_propagate_desc))
+        return fail(PSB_ERR_INVALID, "psb_propagate_ex: descriptor size mismatch (header / library version skew)");
+    const psb_propagate_desc& d = *dp;
+    const psb_c64* t = d.t;
+    const float* phase = d.phase;
+    const int n_frames = d.n_frames, n_probes = d.n_probes, nz = d.nz, nx = d.nx, ny = d.ny, mode = d.mode;
+    if (!d.probes || (!t && !phase) || (t && phase) || !d.prop_x || !d.prop_y || !d.psi_work)
+        return fail(PSB_ERR_INVALID, "psb_propagate: null pointer (or both t and phase given)");
+    if (phase && !d.t0_scratch) return fail(PSB_ERR_INVALID, "psb_propagate_phase: t0 scratch required");
+    if (mode < 0 || mode > 2) return fail(PSB_ERR_INVALID, "psb_propagate: mode must be 0, 1 or 2");
+    if (mode == 1 && !d.wf_out) return fail(PSB_ERR_INVALID, "psb_propagate: wf_out required in mode 1");
+    if (mode == 2 && (!d.det_mask || !d.det_out || !d.det_scratch))
+        return fail(PSB_ERR_INVALID, "psb_propagate: det_mask, det_out and det_scratch required in mode 2");
+    if (n_frames < 0 || n_probes < 1 || nz < 1 || nx < 1 || ny < 1 || d.layer_every < 0)
+        return fail(PSB_ERR_INVALID, "psb_propagate: bad sizes");
+    const bool slabs = mode == 1 && d.slab_world > 1;
+    if (slabs && (d.slab_world > nx || d.slab_layers < 1 || d.slab_frames < 1 || d.slab_probes < 1 || d.frame0 < 0 || d.probe0 < 0 ||
+                  d.frame0 + n_frames > d.slab_frames || d.probe0 + n_probes > d.slab_probes))
+        return fail(PSB_ERR_INVALID, "psb_propagate: bad slab layout");
+    const long long n_img_ll = (long long)n_frames * n_probes;
+    if (n_img_ll == 0) return PSB_OK;
+    cudaStream_t s = as_stream(d.stream);
+    const long long img = (long long)nx * ny;
+    // the generic passes put the image index in gridDim.y: larger batches go through in slices of whole frames
+    if (n_img_ll > 65535) {
+        const int fmax = 65535 / n_probes;
+        if (fmax < 1) return fail(PSB_ERR_UNSUPPORTED, "psb_propagate: more than 65535 probes per call");
+        for (int f0 = 0; f0 < n_frames; f0 += fmax) {
+            psb_propagate_desc part = d;
+            part.n_frames = n_frames - f0 < fmax ? n_frames - f0 : fmax;
+            if (t) part.t = t + (long long)f0 * nz * img;
+            if (phase) part.phase = phase + (long long)f0 * nz * img;
+            if (mode == 1 && !slabs) part.wf_out = d.wf_out + (long long)f0 * d.stride_frame;
+            part.psi_work = d.psi_work + (long long)f0 * n_probes * img;          // mode 0 leaves its result there
+            part.frame0 = d.frame0 + f0;
+            int rc = psb_propagate_ex(&part);
+            if (rc != PSB_OK) return rc;
+        }
+        return PSB_OK;
+    }
+    // same buffers and sizes as an earlier call -> the recorded launch sequence (two kernels per slice) replays as one graph
+    auto eager = [&](cudaStream_t ls) { return propagate_eager(d, ls); };
+#ifndef PSB_EMU
+    struct Key {
+        psb_propagate_desc d;
+        int level, tag;
+    } key;
+    std::memset(&key, 0, sizeof(key));
+    std::memcpy(&key.d, &d, sizeof(d));          // includes padding bytes of d, which callers zero (memset / ctypes)
+    key.d.stream = nullptr;
+    key.level = fast_path_level(); key.tag = 0x70726f70;
+    return run_graphed(&key, sizeof(key), s, eager);
+#else
+    return eager(s);
+#endif
 }
 
 static psb_propagate_desc dense_desc(const psb_c64* probes, int n_frames, int n_probes, int nz, int nx, int ny, const psb_c64* prop_x,

@@ -35,9 +35,11 @@ int launch_fast_rows_phase_out(float2* pairs, int n_img, int nx, int ny, float s
 // structure-factor sum of slice pairs [pair_begin, pair_begin + pair_count) of nf frames into out (nf, pair_count, nx, ny)
 // (sf_fast.cu: precomputed phase tables + TMA-fed packed-FMA tiles); any grid size
 // sf_fast_prepare gathers the form-factor table once per psb_build_transmission call; launch_sf_fast runs per chunk
-int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s);
+// `s` receives the launches; the workspaces are kept per (device, `owner` stream) -- the caller's stream, which differs from
+// `s` only while the sequence is being recorded into a graph on the library's capture stream
+int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s, cudaStream_t owner);
 int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
-                   int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s);
+                   int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s, cudaStream_t owner);
 void sf_fast_release();
 bool sf_fast_supported(int ntypes);      // the pipelined kernel stages at most 64 atom types; beyond that the generic kernel runs
 

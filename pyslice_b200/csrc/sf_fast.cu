@@ -17,6 +17,7 @@
 // The tables stay L2-resident between K1 and K2 (a few MB per chunk).
 #include "fast_fft.cuh"
 #include "fast_path.h"
+#include "graph_cache.h"
 #include "pdl.cuh"
 #include "potential_kernels.cuh"
 #include "psb_rt.h"
@@ -407,15 +408,16 @@ const float4* sf_fast_ff4(cudaStream_t s) {
     return reinterpret_cast<const float4*>(workspace_of(s).ff4);
 }
 
-int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s) {
+int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s, cudaStream_t owner) {
     const size_t n = (size_t)ntypes * StructureFactorPaired::slots(nx) * StructureFactorPaired::slots(ny);
     float4* ff4 = nullptr;
     {
         std::lock_guard<std::mutex> lk(g_ws_mu);
-        SfWorkspace& w = workspace_of(s);
+        SfWorkspace& w = workspace_of(owner);
         if (n * sizeof(float4) > w.ff4_bytes) {
-            cudaError_t e = cudaStreamSynchronize(s);
+            cudaError_t e = cudaStreamSynchronize(owner);
             if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf workspace sync: ") + cudaGetErrorString(e));
+            graph_cache_release();                         // recorded launch sequences point at the block freed here
             rt::dev_free(w.ff4);
             w.ff4 = rt::dev_alloc(n * sizeof(float4));
             w.ff4_bytes = w.ff4 ? n * sizeof(float4) : 0;
@@ -434,7 +436,7 @@ int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s)
 bool sf_fast_supported(int ntypes) { return ntypes <= kMaxStagedTypes; }
 
 int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
-                   int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s) {
+                   int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s, cudaStream_t owner) {
     SfFastParams p;
     std::memset(&p, 0, sizeof(p));
     p.offsets = offsets; p.ux = ux; p.uy = uy; p.cap = cap; p.nz = nz; p.ntypes = ntypes; p.nx = nx; p.ny = ny;
@@ -447,10 +449,11 @@ int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned in
     const size_t need = (nx_elems + ny_elems) * sizeof(float2) + 2 * sn_elems * sizeof(float) + 256;
     {
         std::lock_guard<std::mutex> lk(g_ws_mu);
-        SfWorkspace& w = workspace_of(s);
+        SfWorkspace& w = workspace_of(owner);
         if (need > w.ws_bytes) {
-            cudaError_t e = cudaStreamSynchronize(s);      // kernels of earlier chunks may still read the old block
+            cudaError_t e = cudaStreamSynchronize(owner);  // kernels of earlier chunks may still read the old block
             if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("sf workspace sync: ") + cudaGetErrorString(e));
+            graph_cache_release();                         // recorded launch sequences point at the block freed here
             rt::dev_free(w.ws);
             w.ws = rt::dev_alloc(need);
             w.ws_bytes = w.ws ? need : 0;

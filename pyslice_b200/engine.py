@@ -87,6 +87,11 @@ def set_fast_path(enable) -> None:
     _lib.lib().psb_set_fast_path(level)
 
 
+def set_graph_mode(on: bool) -> None:
+    """CUDA-graph replay of repeated launch sequences inside libpsb (default on); off = every kernel launched directly."""
+    _lib.lib().psb_set_graph_mode(1 if on else 0)
+
+
 def _device(device=None) -> torch.device:
     if _lib.is_emulated():                       # tests/emu only
         return torch.device("cpu")
@@ -206,16 +211,27 @@ def fft2(x: torch.Tensor, inverse: bool = False, scale: float = 1.0, out: Option
     return out
 
 
-def bin_atoms(plan: SlicePlan, positions: torch.Tensor):
+def bin_buffers(plan: SlicePlan, F: int, A: int):
+    """scratch + outputs of psb_bin_atoms for up to F frames of A atoms (allocate once per run: stable addresses let
+    libpsb replay the potential build of later batches as a recorded graph)"""
+    dev = plan.device
+    nseg = plan.nz * plan.ntypes
+    return dict(F=F, A=A,
+                seg=torch.empty((F * (4 * A + nseg),), dtype=torch.int32, device=dev),     # seg ids + unsorted lists + cursors
+                offsets=torch.empty((F, nseg + 1), dtype=torch.int32, device=dev),
+                atom_list=torch.empty((F, 2 * A), dtype=torch.int32, device=dev),
+                ux=torch.empty((F, 2 * A), dtype=torch.int32, device=dev),
+                uy=torch.empty((F, 2 * A), dtype=torch.int32, device=dev))
+
+
+def bin_atoms(plan: SlicePlan, positions: torch.Tensor, buffers=None):
     """positions (F, A, 3) float64 on device -> (offsets (F, nseg+1), atom_list, ux, uy (F, 2A))."""
     F, A, _ = positions.shape
     dev = plan.device
-    nseg = plan.nz * plan.ntypes
-    seg = torch.empty((F * (4 * A + nseg),), dtype=torch.int32, device=dev)     # seg ids + unsorted lists + cursors
-    offsets = torch.empty((F, nseg + 1), dtype=torch.int32, device=dev)
-    atom_list = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
-    ux = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
-    uy = torch.empty((F, 2 * A), dtype=torch.int32, device=dev)
+    if buffers is None or buffers["F"] < F or buffers["A"] != A:
+        buffers = bin_buffers(plan, F, A)
+    seg = buffers["seg"]
+    offsets, atom_list, ux, uy = (buffers[k][:F] for k in ("offsets", "atom_list", "ux", "uy"))
     L = _lib.lib()
     with _on(dev):
         _lib.check(L.psb_bin_atoms(positions.data_ptr(), plan.type_idx.data_ptr(), F, A, plan.ntypes, plan.nz,
@@ -251,12 +267,14 @@ def phase_format_supported(plan: SlicePlan) -> bool:
 
 
 def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential: bool = False,
-                       out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None, phase: bool = False):
+                       out: Optional[torch.Tensor] = None, scratch: Optional[torch.Tensor] = None, phase: bool = False,
+                       bins=None):
     """positions (F, A, 3) float64 on device -> t (F, nz, nx, ny) complex64 [, V float32].
-    phase=True: the stack as float32 phases sigma*V instead (half the bytes; `propagate` accepts either)."""
+    phase=True: the stack as float32 phases sigma*V instead (half the bytes; `propagate` accepts either).
+    bins: optional `bin_buffers` to reuse across calls."""
     F, A, _ = positions.shape
     dev = plan.device
-    offsets, _, ux, uy = bin_atoms(plan, positions)
+    offsets, _, ux, uy = bin_atoms(plan, positions, bins)
     scale = 1.0 / (plan.dx ** 2 * plan.dy ** 2)
     img = plan.nx * plan.ny
     n_scratch = img * chunk_images(plan, F)
@@ -270,7 +288,7 @@ def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential:
         with _on(dev):
             _lib.check(L.psb_build_phase(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
                                          plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
-                                         ph.data_ptr(), scratch.data_ptr(), scratch.numel(), _stream(dev)), "psb_build_phase")
+                                         ph.data_ptr(), scratch.data_ptr(), n_scratch, _stream(dev)), "psb_build_phase")
         return ph
     t = out if out is not None else torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device=dev)
     V = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32, device=dev) if want_potential else None
@@ -278,7 +296,7 @@ def build_transmission(plan: SlicePlan, positions: torch.Tensor, want_potential:
         _lib.check(L.psb_build_transmission(offsets.data_ptr(), ux.data_ptr(), uy.data_ptr(), F, A, plan.nz, plan.ntypes,
                                             plan.nx, plan.ny, plan.formfactors.data_ptr(), scale, plan.sigma,
                                             t.data_ptr(), V.data_ptr() if V is not None else None, scratch.data_ptr(),
-                                            scratch.numel(), _stream(dev)),
+                                            n_scratch, _stream(dev)),
                    "psb_build_transmission")
     return (t, V) if want_potential else t
 
@@ -319,7 +337,7 @@ def row_split(n: int, world: int):
 
 def propagate(plan: SlicePlan, probes: torch.Tensor, t: torch.Tensor, wf_out: Optional[torch.Tensor] = None,
               frame0: int = 0, probe0: int = 0, layer_every: int = 0, work: Optional[torch.Tensor] = None,
-              slabs=None, detector=None):
+              slabs=None, detector=None, t0: Optional[torch.Tensor] = None):
     """Push `probes` (P, nx, ny) through the transmission stack `t` (F, nz, nx, ny; complex64 t or float32 phases).
 
     wf_out is None: returns the real-space exit waves (F, P, nx, ny)  (the reference's Propagate()).
@@ -344,7 +362,8 @@ def propagate(plan: SlicePlan, probes: torch.Tensor, t: torch.Tensor, wf_out: Op
     d.psi_work = work.data_ptr()
     d.stream = _stream(plan.device)
     if t.dtype == torch.float32:                 # phase stack (build_transmission(phase=True))
-        t0 = torch.empty((F, nx, ny), dtype=torch.complex64, device=plan.device)
+        if t0 is None or t0.numel() < F * nx * ny:
+            t0 = torch.empty((F, nx, ny), dtype=torch.complex64, device=plan.device)
         d.phase, d.t0_scratch = t.data_ptr(), t0.data_ptr()
     else:
         d.t = t.data_ptr()

@@ -225,6 +225,11 @@ class MultisliceCalculator:
             params['positions_sha1'] = hashlib.sha1(np.ascontiguousarray(pos, dtype=np.float64).tobytes()).hexdigest()
         return hashlib.md5(str(sorted(params.items())).encode()).hexdigest()[:12]
 
+    def release_workspace(self) -> None:
+        """drop the per-batch device buffers kept between run() calls (the transmission stack of one frame batch, psi work
+        area, binning scratch)"""
+        self._workspace = None
+
     def _cache_file(self, frame: int) -> Path:
         return self.output_dir / f"frame_{frame}.npy"
 
@@ -246,8 +251,21 @@ class MultisliceCalculator:
         # one probe per frame: the stack is written once and read once, so it is kept as float32 phases (half the HBM
         # traffic, exp(i*phase) evaluated inside the fused slice step); shared by several probes it stays complex64
         use_phase = P == 1 and engine.phase_format_supported(plan)
-        tbuf = torch.empty((fb, plan.nz, nx, ny), dtype=torch.float32 if use_phase else torch.complex64, device=self.device)
-        work = torch.empty((fb * min(pb, P), nx, ny), dtype=torch.complex64, device=self.device)
+        # Per-batch workspaces live on the calculator and are reused by every batch and every later run(): besides saving
+        # the allocations, stable addresses let libpsb replay a batch's ~2000 launches as recorded CUDA graphs
+        # (graph_cache.cu).  release_workspace() frees them.
+        A = int(self.trajectory.positions.shape[1])
+        ws_key = (fb, pb, P, nx, ny, plan.nz, use_phase, A)
+        ws = getattr(self, "_workspace", None)
+        if ws is None or ws["key"] != ws_key:
+            ws = dict(key=ws_key,
+                      tbuf=torch.empty((fb, plan.nz, nx, ny), dtype=torch.float32 if use_phase else torch.complex64, device=self.device),
+                      work=torch.empty((fb * min(pb, P), nx, ny), dtype=torch.complex64, device=self.device),
+                      t0=torch.empty((fb, nx, ny), dtype=torch.complex64, device=self.device) if use_phase else None,
+                      scratch=torch.empty((nx * ny * engine.chunk_images(plan, fb),), dtype=torch.complex64, device=self.device),
+                      bins=engine.bin_buffers(plan, fb, A))
+            self._workspace = ws
+        tbuf, work = ws["tbuf"], ws["work"]
         # the result store is allocated AFTER the multi-GB stack: while a previous result is still alive the caching
         # allocator would otherwise carve the new store out of the cached stack block and then cudaMalloc a fresh stack
         # (tens of milliseconds of idle GPU, seen as random gaps between the phases of repeated runs)
@@ -326,12 +344,12 @@ class MultisliceCalculator:
                 pos = np.ascontiguousarray(block, dtype=np.float64)
                 pos_d = torch.from_numpy(pos).to(self.device, non_blocking=True)
             with timer.phase("potential"):
-                t = engine.build_transmission(plan, pos_d, out=tbuf[:nb], phase=use_phase)
+                t = engine.build_transmission(plan, pos_d, out=tbuf[:nb], phase=use_phase, scratch=ws["scratch"], bins=ws["bins"])
             with timer.phase("propagate"):
                 for p0 in range(0, P, pb):
                     np_ = min(pb, P - p0)
                     engine.propagate(plan, self._probes[p0:p0 + np_], t, wf_out=store, frame0=b0, probe0=p0,
-                                     layer_every=self.layer_every, work=work, detector=det,
+                                     layer_every=self.layer_every, work=work, detector=det, t0=ws["t0"],
                                      slabs=(world, self.n_layers, T_loc, P) if slabs else None)
             if writer is not None:
                 host = store[0, :, b0:b0 + nb].to("cpu")                 # (P, nb, nx, ny); synchronises this batch

@@ -563,3 +563,45 @@ def test_phase_stack_equals_complex_stack(box, grid):
     assert not engine.phase_format_supported(splan)
     with pytest.raises(_lib.PsbError):
         engine.build_transmission(splan, dev(small.positions), phase=True)
+
+
+def test_graph_replay_is_bit_identical_and_survives_workspace_growth():
+    """CUDA-graph replay inside libpsb (graph_cache.cu): the third and later calls with the same buffers replay the recorded
+    launch sequence.  Results must equal direct launches bit for bit -- phase stack, exit waves, layer taps -- also after a
+    larger job in between made the structure-factor workspace grow (recorded graphs pointing at the old block are dropped)."""
+    from pyslice_b200 import engine, synthetic
+    from pyslice_b200.multislice.calculators import MultisliceCalculator
+    traj = synthetic.random_trajectory(n_atoms=500, box=(25.55, 25.55, 5.1), n_frames=6, seed=77, types=(6, 14))
+    big = synthetic.random_trajectory(n_atoms=4000, box=(25.55, 25.55, 5.1), n_frames=6, seed=78, types=(6, 14, 31))
+    pp = [(3.0, 4.0), (12.5, 20.0)]
+
+    def runs(calc, n):
+        return [calc.run().wavefunction_data.clone() for _ in range(n)]
+
+    engine.set_graph_mode(False)
+    try:
+        ref = MultisliceCalculator()
+        ref.setup(traj, aperture=0.0, voltage_eV=100e3, layer_every=4)
+        want = runs(ref, 1)[0]
+        ref2 = MultisliceCalculator()
+        ref2.setup(traj, aperture=25.0, voltage_eV=100e3, probe_positions=pp)
+        want2 = runs(ref2, 1)[0]
+    finally:
+        engine.set_graph_mode(True)
+    l0 = engine.launch_count()
+    calc = MultisliceCalculator()
+    calc.setup(traj, aperture=0.0, voltage_eV=100e3, layer_every=4)
+    got = runs(calc, 4)                      # eager, capture, replay, replay
+    for g in got:
+        assert torch.equal(g, want)
+    per_run = (engine.launch_count() - l0) // 4
+    assert per_run > 20                      # replayed launches are still counted
+    calc2 = MultisliceCalculator()
+    calc2.setup(traj, aperture=25.0, voltage_eV=100e3, probe_positions=pp)
+    for g in runs(calc2, 3):
+        assert torch.equal(g, want2)
+    other = MultisliceCalculator()           # more atoms per frame: the phase-table workspace grows
+    other.setup(big, aperture=0.0, voltage_eV=100e3)
+    runs(other, 3)
+    for g in runs(calc, 3):                  # the small job again, through graphs recorded afresh
+        assert torch.equal(g, want)
