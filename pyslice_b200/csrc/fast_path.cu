@@ -360,12 +360,17 @@ constexpr int kColCtasPerSm = kColXBufs == 1 ? 3 : 2;
 #ifndef PSB_COL1024_THREADS
 #define PSB_COL1024_THREADS 512
 #endif
+// 512-point columns: 256 threads and 8-column tiles (64-byte global segments) in two CTAs per SM (default), or 512 threads
+// and 16-column tiles (128-byte segments) in one CTA per SM (-DPSB_COL512_THREADS=512)
+#ifndef PSB_COL512_THREADS
+#define PSB_COL512_THREADS 256
+#endif
 
 template <int N>
 struct ColCfg {
     static constexpr int T = N / 16;
-    static constexpr int kThreads = N == 1024 ? PSB_COL1024_THREADS : 256;
-    static constexpr int kCtasPerSm = N == 1024 ? (kThreads == 512 ? 1 : 2) : kColCtasPerSm;
+    static constexpr int kThreads = N == 1024 ? PSB_COL1024_THREADS : (N == 512 ? PSB_COL512_THREADS : 256);
+    static constexpr int kCtasPerSm = N == 1024 ? (kThreads == 512 ? 1 : 2) : ((N == 512 && kThreads == 512) ? 1 : kColCtasPerSm);
     static constexpr int W = kThreads / T;                            // columns per tile: 16 (N=256), 8 (N=512, 1024), 4 (1024, 256 threads)
     static constexpr int kPadRows = (W < 16) ? N / 16 : 0;            // keeps narrow rows conflict-free
     static constexpr int kLand = N * W;                               // float2 (32 KB; 64 KB for N = 1024)

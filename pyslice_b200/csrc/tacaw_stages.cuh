@@ -5,6 +5,8 @@
 #pragma once
 #include "psb_common.cuh"
 
+#include <cstdlib>
+
 namespace psb {
 namespace tw {
 
@@ -69,7 +71,27 @@ PSB_D void first_stage(unsigned tid, float2* data, const float2* PSB_RESTRICT sr
                                             const float2* PSB_RESTRICT tw, int T) {
     const int sub = T / R;
     const int px = tid % PX;
-    for (int n = tid / PX; n < sub; n += kThreads / PX) {
+    constexpr int step = kThreads / PX;
+    // Two butterflies per trip: the 2*R global loads are all issued before the first butterfly is computed.  With one
+    // butterfly per trip a CTA kept R*kThreads*8 bytes in flight -- about half of what the HBM latency-bandwidth product
+    // asks of an SM (ncu r1j: long-scoreboard stalls 4.0 per issue, 0.61 of the copy bandwidth).
+    int n = tid / PX;
+    for (; n + step < sub; n += 2 * step) {
+        float2 x[R], y[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) x[i] = live ? src[(long long)(n + i * sub) * stride_frame] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < R; ++i) y[i] = live ? src[(long long)(n + step + i * sub) * stride_frame] : make_float2(0.f, 0.f);
+        dft<R>(x);
+        data[n * PX + px] = x[0];
+#pragma unroll
+        for (int k = 1; k < R; ++k) data[(k * sub + n) * PX + px] = cmul(x[k], __ldg(&tw[n * k]));
+        dft<R>(y);
+        data[(n + step) * PX + px] = y[0];
+#pragma unroll
+        for (int k = 1; k < R; ++k) data[(k * sub + n + step) * PX + px] = cmul(y[k], __ldg(&tw[(n + step) * k]));
+    }
+    for (; n < sub; n += step) {
         float2 x[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) x[i] = live ? src[(long long)(n + i * sub) * stride_frame] : make_float2(0.f, 0.f);
@@ -162,8 +184,16 @@ inline void build_perm(int T, const int* fac, int nfac, int* perm) {
     }
 }
 
-// pixels per tile: as many as keep the tile within 96 KB of shared memory (two CTAs per SM), else 8 or 4 with the SM to itself
+// pixels per tile: as many as keep the tile within `tile_kb` of shared memory (default 96 KB: two CTAs per SM; the
+// environment variable PSB_TACAW_TILE_KB overrides it for tuning runs), else 8 or 4 with the SM to itself
 inline int pick_px(int T) {
+    static const size_t tile_kb = [] {
+        const char* e = std::getenv("PSB_TACAW_TILE_KB");
+        const long v = e ? std::atol(e) : 0;
+        return (size_t)(v >= 8 && v <= 96 ? v : 96);
+    }();
+    for (int px : {64, 32, 16, 8})
+        if ((size_t)T * px * sizeof(float2) <= (tile_kb << 10)) return px;
     for (int px : {64, 32, 16, 8})
         if ((size_t)T * px * sizeof(float2) <= (96u << 10)) return px;
     if ((size_t)T * 8 * sizeof(float2) <= (200u << 10)) return 8;
