@@ -50,9 +50,12 @@ ALIASES = {"c1": "c1_si_256x256x103_20f_planewave", "c2": "c2_si_256x256x512_500
 DEFAULT = "c2_si_256x256x512_500f_planewave"
 VOLTAGE = 100e3
 
-# fp32-pipe floor of the fused slice step: lane-cycles per pixel and slice step of the packed radix-16
-# transforms + pointwise multiplies, by line length (both passes; 1024-point lines: radix 16 x 4 x 16)
-FP32_LANE_CYCLES_PER_PIXEL = {256: 112.0, 512: 129.0, 1024: 141.0}
+# fp32 issue floor of the fused slice step: SM-cycles per pixel and slice step that the packed-fp32
+# instructions of the row + column kernels need when nothing else stalls, from their SASS (profiles/r2_sass_mix.txt) at the
+# measured per-instruction cost (profiles/r2_ubench_fp32x2_operands.txt: the register file, not the fma pipe, sets it --
+# FADD2 2.1 cycles per warp and scheduler, FFMA2 2.1 to 3.2 by distinct source registers).  Key: (line length, stack format).
+FP32_SM_CYCLES_PER_PIXEL = {(256, "phase"): 0.499 + 0.478, (256, "c64"): 0.441 + 0.478, (512, "phase"): 0.617 + 0.597,
+                            (512, "c64"): 0.560 + 0.597, (1024, "phase"): 0.622 + 0.601, (1024, "c64"): 0.564 + 0.601}
 
 
 def make_traj(wl, n_frames, frame0=0):
@@ -579,16 +582,17 @@ def main():
                                                                           traffic_doc.get("slice_step_dram_bytes_per_launch") if nx == 256 else None)
         fb = engine.batch_sizes(calc._plan, P, max(F, 1))[0]
         cfg = config_block(wl, name, world, counts, A, P)
-        lanes = FP32_LANE_CYCLES_PER_PIXEL.get(max(nx, ny))
+        cyc = FP32_SM_CYCLES_PER_PIXEL.get((max(nx, ny), "phase" if P == 1 else "c64")) if nx == ny else None
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
         fp32_floor = None
-        if lanes:
-            floor_steps = 148 * 128 * sm_clock * 1e6 / (lanes * nx * ny)        # slice-steps/s with the fp32 pipe 100 % busy
-            fp32_floor = {"lane_cycles_per_pixel": lanes, "slice_steps_per_s_at_full_pipe": floor_steps,
+        if cyc:
+            floor_steps = 148 * sm_clock * 1e6 / (cyc * nx * ny)        # slice-steps/s if the fp32 instructions alone filled the SMs
+            fp32_floor = {"sm_cycles_per_pixel": cyc, "slice_steps_per_s": floor_steps,
                           "frac_of_floor": (per_gpu_steps / (prop_ms * 1e-3)) / floor_steps if prop_ms > 0 else None,
                           "hbm_roofline_slice_steps_per_s": peak * 1e9 / b_ss,
-                          "note": "the transforms' own packed-fp32 instruction count bounds the slice step at this rate "
-                                  "(DESIGN.md 4.1); where it is below the HBM roofline, frac cannot reach 1"}
+                          "max_frac_of_hbm_roofline": floor_steps / (peak * 1e9 / b_ss),
+                          "note": "register-file-limited issue time of the kernels' own packed-fp32 instructions (DESIGN.md 4.1, "
+                                  "profiles/r2_sass_mix.txt); roofline.frac cannot exceed max_frac_of_hbm_roofline with these transforms"}
         line = {
             "metric": "slice-steps/sec (probe*frame*slice)", "value": value, "unit": "slice-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_dev / args.steps,
