@@ -119,6 +119,9 @@ int psb_bin_atoms(const double* positions, const int32_t* type_idx, int n_frames
         rc = go<BinScatter>(dim3((n_atoms + 255) / 256, n_frames), 0, s, p, "bin_scatter");
         if (rc != PSB_OK) return rc;
         rc = go<BinOrder>(dim3((nseg + 7) / 8, n_frames), 0, s, p, "bin_order");
+        if (rc != PSB_OK) return rc;
+        // segments too large for one warp's all-pairs ranking (an upper bound per segment is all the host knows)
+        if (n_atoms > kBinOrderWarpMax) rc = go<BinOrderLarge>(dim3(nseg, n_frames), BinOrderLarge::kSmem, s, p, "bin_order_large");
     }
     return rc;
 }

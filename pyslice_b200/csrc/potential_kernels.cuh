@@ -113,6 +113,22 @@ struct BinScatter {
     }
 };
 
+// segments up to this many atoms are ranked by one warp (BinOrder); larger ones by a whole CTA through shared memory
+// (BinOrderLarge): the all-pairs ranking is O(n^2), fine for the tens of atoms of a bulk-crystal slice, a cliff for the
+// 10^3..10^5 atoms a 2-D material or a thick slice puts into one (slice, type) segment
+constexpr int kBinOrderWarpMax = 64;
+
+PSB_D void bin_emit(const BinParams& p, int f, long long o, int a) {
+    const double* pos = p.pos + (long long)f * p.A * 3;
+    p.atom_list[o] = a;
+    double u = pos[3 * a] * p.inv_lx;
+    double v = pos[3 * a + 1] * p.inv_ly;
+    u -= floor(u);
+    v -= floor(v);
+    p.ux[o] = (unsigned int)((unsigned long long)(u * 4294967296.0 + 0.5) & 0xffffffffull);
+    p.uy[o] = (unsigned int)((unsigned long long)(v * 4294967296.0 + 0.5) & 0xffffffffull);
+}
+
 struct BinOrder {
     static constexpr int kThreads = 256;
     static constexpr int kMinBlocks = 1;
@@ -124,20 +140,57 @@ struct BinOrder {
         const int lane = cx.tid() % 32;
         const int* off = p.offsets + (long long)f * (nseg + 1);
         const int begin = off[seg], n = off[seg + 1] - off[seg];
+        if (n > kBinOrderWarpMax) return;                         // BinOrderLarge's
         const int* tmp = p.unsorted + (long long)f * p.cap + begin;
-        const double* pos = p.pos + (long long)f * p.A * 3;
         for (int i = lane; i < n; i += 32) {
             const int a = tmp[i];
             int rank = 0;
             for (int k = 0; k < n; ++k) rank += tmp[k] < a;       // an atom occurs at most once per segment
-            const long long o = (long long)f * p.cap + begin + rank;
-            p.atom_list[o] = a;
-            double u = pos[3 * a] * p.inv_lx;
-            double v = pos[3 * a + 1] * p.inv_ly;
-            u -= floor(u);
-            v -= floor(v);
-            p.ux[o] = (unsigned int)((unsigned long long)(u * 4294967296.0 + 0.5) & 0xffffffffull);
-            p.uy[o] = (unsigned int)((unsigned long long)(v * 4294967296.0 + 0.5) & 0xffffffffull);
+            bin_emit(p, f, (long long)f * p.cap + begin + rank, a);
+        }
+    }
+};
+
+// One CTA per (segment, frame) with more than kBinOrderWarpMax atoms: the ids are staged in shared memory in chunks and
+// every thread ranks kPer atoms at a time against a chunk (one broadcast read per kPer compares).
+struct BinOrderLarge {
+    static constexpr int kThreads = 256;
+    static constexpr int kMinBlocks = 1;
+    static constexpr int kChunk = 2048;
+    static constexpr int kPer = 4;
+    static constexpr size_t kSmem = kChunk * sizeof(int);
+    template <class Ctx>
+    static PSB_D void run(const Ctx& cx, const BinParams& p) {
+        const int nseg = p.nz * p.ntypes;
+        const int seg = cx.bx(), f = cx.by();
+        const int* off = p.offsets + (long long)f * (nseg + 1);
+        const int begin = off[seg], n = off[seg + 1] - off[seg];
+        if (n <= kBinOrderWarpMax) return;
+        const int* tmp = p.unsorted + (long long)f * p.cap + begin;
+        int* sm = reinterpret_cast<int*>(cx.smem());
+        const int t = cx.tid();
+        for (int a0 = 0; a0 < n; a0 += kThreads * kPer) {
+            int a[kPer], rank[kPer];
+#pragma unroll
+            for (int i = 0; i < kPer; ++i) {
+                const int idx = a0 + i * kThreads + t;
+                a[i] = idx < n ? tmp[idx] : 0x7fffffff;
+                rank[i] = 0;
+            }
+            for (int c0 = 0; c0 < n; c0 += kChunk) {
+                const int m = n - c0 < kChunk ? n - c0 : kChunk;
+                cx.sync();
+                for (int k = t; k < m; k += kThreads) sm[k] = tmp[c0 + k];
+                cx.sync();
+                for (int k = 0; k < m; ++k) {
+                    const int v = sm[k];
+#pragma unroll
+                    for (int i = 0; i < kPer; ++i) rank[i] += v < a[i];
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < kPer; ++i)
+                if (a0 + i * kThreads + t < n) bin_emit(p, f, (long long)f * p.cap + begin + rank[i], a[i]);
         }
     }
 };

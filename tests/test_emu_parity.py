@@ -33,6 +33,25 @@ def membership(plan, offsets, atom_list, n_atoms):
     return m
 
 
+def test_binning_of_crowded_segments():
+    """(slice, type) segments with hundreds of atoms (a 2-D material, a thick slice): the CTA-wide ranking of
+    BinOrderLarge orders them like the one-warp kernel orders small ones -- ascending atom index, memberships exact"""
+    from pyslice_b200 import engine, hostmath, synthetic
+    traj = synthetic.random_trajectory(n_atoms=700, box=(1.55, 1.55, 1.2), n_frames=2, seed=19, types=(6,), stray=True)
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    offsets, atom_list, ux, uy = engine.bin_atoms(plan, torch.from_numpy(traj.positions.copy()))
+    assert int((offsets[0, 1:] - offsets[0, :-1]).max()) > 64
+    for f in range(2):
+        want = orc.bin_atoms(traj.positions[f][:, 2], zs)
+        assert np.array_equal(membership(plan, offsets[f], atom_list[f], traj.n_atoms), want)
+        n = int(offsets[f, -1])
+        ids = atom_list[f, :n].numpy()
+        u = traj.positions[f][ids, 0] / (plan.nx * plan.dx)
+        want_u = ((np.floor((u - np.floor(u)) * 4294967296.0 + 0.5)).astype(np.uint64) & 0xffffffff).astype(np.uint32)
+        assert np.array_equal(ux[f, :n].numpy().view(np.uint32), want_u)
+
+
 @pytest.mark.parametrize("shape", [(16, 16), (32, 64), (48, 40), (20, 36), (128, 16)])
 def test_fft2_kernels(shape):
     from pyslice_b200 import engine
