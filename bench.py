@@ -204,8 +204,9 @@ def reference_sample_frames(wl, name, target_s=12.0):
     container takes 3.6 s on 8)"""
     key = (name, wl["frames"])
     if key not in _PILOT:
-        _, d = reference_torch_step(wl, name, n_frames=2)
-        _PILOT[key] = d["seconds"] / 2
+        reference_torch_step(wl, name, n_frames=2)                       # start-up costs (thread pool, imports, page cache)
+        _, d = reference_torch_step(wl, name, n_frames=min(6, max(2, wl["frames"])))
+        _PILOT[key] = d["seconds"] / max(2, min(6, wl["frames"]))
     per_frame = _PILOT[key]
     return int(max(2, min(96, wl["frames"], round(target_s / max(per_frame, 1e-3)))))
 

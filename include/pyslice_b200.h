@@ -49,6 +49,10 @@ void psb_set_fast_path(int level);
  * psb_propagate_ex / psb_propagate / psb_propagate_phase and psb_build_transmission / psb_build_phase called again with the
  * same buffers and sizes replay the ~1000 launches of a batch as one graph launch.  Results are identical either way. */
 void psb_set_graph_mode(int on);
+/* structure-factor algorithm of psb_build_transmission / psb_build_phase: 0 = automatic (default: the direct sum, or the
+ * 1-D NUFFT of csrc/sf_nufft.cu for dense slices on 1024-point grids), 1 = direct sum always, 2 = NUFFT wherever it is
+ * implemented (nx = 512 or 1024).  Both build the same spectrum to float32 round-off. */
+void psb_set_sf_mode(int mode);
 
 /* ---- atom -> slice binning: src/multislice/potentials.py:297-317 (+ bounds :304-305) -------------
  * positions (F, A, 3) float64; type_idx (A) dense type index in [0, ntypes);

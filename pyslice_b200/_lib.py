@@ -46,6 +46,7 @@ _SIGNATURES = {
     "psb_launch_count": (C.c_longlong, []),
     "psb_set_fast_path": (None, [_I]),
     "psb_set_graph_mode": (None, [_I]),
+    "psb_set_sf_mode": (None, [_I]),
     "psb_bin_atoms": (C.c_int, [_P, _P, _I, _I, _I, _I, _P, _P, _D, _D, _D, _P, _P, _P, _P, _P, _P]),
     "psb_build_transmission": (C.c_int, [_P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _F, _F, _P, _P, _P, _LL, _P]),
     "psb_transmission_from_potential": (C.c_int, [_P, _P, _LL, _F, _P]),

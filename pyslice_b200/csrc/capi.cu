@@ -78,6 +78,13 @@ void psb_set_graph_mode(int on) {
     (void)on;
 #endif
 }
+void psb_set_sf_mode(int mode) {
+#ifndef PSB_EMU
+    sf_mode_set(mode);
+#else
+    (void)mode;
+#endif
+}
 void psb_set_fast_path(int level) {
 #ifndef PSB_EMU
     fast_path_enable(level);
@@ -164,7 +171,8 @@ static int build_eager(const int32_t* offsets, const uint32_t* ux, const uint32_
     const int tiles = ((StructureFactorPaired::slots(nx) + TXs - 1) / TXs) * ((StructureFactorPaired::slots(ny) + TYs - 1) / TYs);
 #ifndef PSB_EMU
     // pipelined structure factor (sf_fast.cu) unless the type count exceeds what it stages: then the generic kernel
-    const bool sf_fast = fast_path_enabled() && sf_fast_supported(ntypes);
+    const bool sf_nufft = fast_path_enabled() && fast_slice_supported(nx, ny) && sf_nufft_wanted(ntypes, nx, ny, n_atoms, nz);
+    const bool sf_fast = !sf_nufft && fast_path_enabled() && sf_fast_supported(ntypes);
     if (sf_fast) {
         int rc0 = sf_fast_prepare(formfactors, ntypes, nx, ny, s, owner);
         if (rc0 != PSB_OK) return rc0;
@@ -200,7 +208,9 @@ static int build_eager(const int32_t* offsets, const uint32_t* ux, const uint32_
             groups = (nm + sp.pairs_per_block - 1) / sp.pairs_per_block;
             int rc;
 #ifndef PSB_EMU
-            if (sf_fast)
+            if (sf_nufft)
+                rc = launch_sf_nufft(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, formfactors, f2(scratch), s, owner);
+            else if (sf_fast)
                 rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, f2(scratch), s, owner);
             else
 #endif
@@ -255,7 +265,7 @@ static int build_impl(const int32_t* offsets, const uint32_t* ux, const uint32_t
     key.offsets = offsets; key.ux = ux; key.uy = uy; key.ff = formfactors; key.t_out = t_out; key.v_out = v_out;
     key.phase_out = phase_out; key.scratch = scratch; key.owner = owner; key.scratch_elems = scratch_elems;
     key.n_frames = n_frames; key.n_atoms = n_atoms; key.nz = nz; key.ntypes = ntypes; key.nx = nx; key.ny = ny;
-    key.level = fast_path_level(); key.tag = 0x6275696c;
+    key.level = fast_path_level() * 8 + sf_mode(); key.tag = 0x6275696c;
     key.scale = scale; key.sigma = sigma;
     return run_graphed(&key, sizeof(key), owner, eager);
 #else

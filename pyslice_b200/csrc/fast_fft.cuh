@@ -1,4 +1,4 @@
-// Line FFTs of the fused slice-step kernels (fast_path.cu): N = 256, 512 or 1024 complex64 points held by
+// Line FFTs of the fused kernels (fast_path.cu, sf_nufft.cu): N = 256, 512, 1024 or 2048 complex64 points held by
 // T = N/16 threads, 16 points per thread in the strided register layout of fft_core.cuh
 // (thread j owns positions j + e*T), built for Blackwell's packed fp32 pipe:
 //
@@ -123,6 +123,22 @@ PSB_D void radix2(cpx& a0, cpx& a1) {
     a1 = d;
 }
 
+// 8-point DFT in place (2 x 4 Cooley-Tukey: n = 2*n1 + n2, k = k1 + 4*k2), natural order in and out
+template <int DIR>
+PSB_D void radix8(cpx (&a)[8]) {
+    cpx e0 = a[0], e1 = a[2], e2 = a[4], e3 = a[6];      // n2 = 0
+    cpx o0 = a[1], o1 = a[3], o2 = a[5], o3 = a[7];      // n2 = 1
+    radix4<DIR>(e0, e1, e2, e3);
+    radix4<DIR>(o0, o1, o2, o3);
+    o1 = rot16<2, DIR>(o1);                               // W8^1
+    o2 = rot16<4, DIR>(o2);                               // W8^2
+    o3 = rot16<6, DIR>(o3);                               // W8^3
+    a[0] = add2(e0, o0); a[4] = sub2(e0, o0);
+    a[1] = add2(e1, o1); a[5] = sub2(e1, o1);
+    a[2] = add2(e2, o2); a[6] = sub2(e2, o2);
+    a[3] = add2(e3, o3); a[7] = sub2(e3, o3);
+}
+
 // 16-point DFT (4 x 4 Cooley-Tukey: n = 4*n1 + n2, k = k1 + 4*k2) as a stream: `in(idx)` produces input idx when
 // the first butterfly layer needs it, `out(idx, value)` takes output idx as soon as the second layer has it.
 // Fusing the loads / pointwise multiplies / stores of a pass into these functors keeps only a few of the 16
@@ -154,17 +170,19 @@ PSB_D void radix16_io(const In& in, const Out& out) {
 //                                (the radix-2 stage is folded into the last stage's loads, see line_fft)
 // N = 1024 (radix 16 x 4 x 16):  w[t-1] = exp(-2*pi*i*j*t/1024), w4[t-1] = exp(-2*pi*i*(j & 15)*t/64), t = 1..3
 //                                (the radix-4 stage runs in place in the exchange buffer, see line_fft)
+// N = 2048 (radix 16 x 8 x 16):  w[t-1] = exp(-2*pi*i*j*t/2048), w4[t-1] = exp(-2*pi*i*(j & 15)*t/128), t = 1..7
 template <int N>
 struct Twiddles {
     cpx w[15];
     cpx w2;
-    cpx w4[3];
+    cpx w4[N == 2048 ? 7 : 3];
     // `staged` is the staged table of Plan<N, 16> built by tables.cu (layout: fft_core.cuh twiddle_offset)
     PSB_D void load(const float2* PSB_RESTRICT staged_f2, int j) {
         const cpx* PSB_RESTRICT staged = reinterpret_cast<const cpx*>(staged_f2);
-        static_assert(N == 256 || N == 512 || N == 1024, "fast path line sizes");
+        static_assert(N == 256 || N == 512 || N == 1024 || N == 2048, "fast path line sizes");
         w2 = c_make(1.f, 0.f);
-        w4[0] = w4[1] = w4[2] = w2;
+#pragma unroll
+        for (int t = 0; t < (N == 2048 ? 7 : 3); ++t) w4[t] = w2;
         if constexpr (N == 256) {
 #pragma unroll
             for (int t = 1; t < 16; ++t) w[t - 1] = staged[(t - 1) * 16 + j];
@@ -172,11 +190,16 @@ struct Twiddles {
             w2 = staged[j & 15];                                           // stage 2 block: R = 2, NS = 16
 #pragma unroll
             for (int t = 1; t < 16; ++t) w[t - 1] = staged[16 + (t - 1) * 32 + j];   // stage 3 block: NS = 32
-        } else {
+        } else if constexpr (N == 1024) {
 #pragma unroll
             for (int t = 1; t < 4; ++t) w4[t - 1] = staged[(t - 1) * 16 + (j & 15)];  // stage 2 block: R = 4, NS = 16
 #pragma unroll
             for (int t = 1; t < 16; ++t) w[t - 1] = staged[48 + (t - 1) * 64 + j];   // stage 3 block: NS = 64
+        } else {
+#pragma unroll
+            for (int t = 1; t < 8; ++t) w4[t - 1] = staged[(t - 1) * 16 + (j & 15)];  // stage 2 block: R = 8, NS = 16
+#pragma unroll
+            for (int t = 1; t < 16; ++t) w[t - 1] = staged[112 + (t - 1) * 128 + j]; // stage 3 block: NS = 128
         }
     }
 };
@@ -230,14 +253,34 @@ PSB_D void line_fft(const In& in, const Out& out, const Twiddles<N>& tw, int j, 
         }
         x.mid_sync(xi0);
     }
+    if constexpr (N == 2048) {
+        // The same with radix 8 (T = 128 threads, two butterflies per thread): butterfly m reads b + 256*t, b = j + 128*m,
+        // twiddle exp(-+2*pi*i*(j & 15)*t/128); output u returns to the slot of input u.  The last stage finds logical
+        // position j + 128*t in slot (j & 15) + 16*(t & 7) + 128*(t >> 3) + 256*(j >> 4).
+        cpx* sm = x.buf(xi0);
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+            const int b = j + 128 * m;
+            cpx a[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) a[t] = sm[x.at(b + 256 * t)];
+#pragma unroll
+            for (int t = 1; t < 8; ++t) a[t] = DIR < 0 ? cmulp(a[t], tw.w4[t - 1]) : cmulcp(a[t], tw.w4[t - 1]);
+            radix8<DIR>(a);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) sm[x.at(b + 256 * t)] = a[t];
+        }
+        x.mid_sync(xi0);
+    }
     // last stage: radix 16 with the thread's own twiddles; outputs come out in natural strided order
     const cpx* sl = x.buf(xi0);
     before_last();
-    if constexpr (N == 1024) {
+    if constexpr (N == 1024 || N == 2048) {
+        constexpr int R2 = N / 256;                  // radix of the middle stage
         const int slot0 = (j & 15) + 256 * (j >> 4);
         radix16_io<DIR>(
             [&](int t) {
-                const cpx a = sl[x.at(slot0 + 16 * (t & 3) + 64 * (t >> 2))];
+                const cpx a = sl[x.at(slot0 + 16 * (t % R2) + T * (t / R2))];
                 if (t == 0) return a;
                 return DIR < 0 ? cmulp(a, tw.w[t > 0 ? t - 1 : 0]) : cmulcp(a, tw.w[t > 0 ? t - 1 : 0]);
             },

@@ -41,6 +41,17 @@ int sf_fast_prepare(const float* ff, int ntypes, int nx, int ny, cudaStream_t s,
 int launch_sf_fast(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
                    int ny, int pair_begin, int pair_count, int nf, float2* out, cudaStream_t s, cudaStream_t owner);
 void sf_fast_release();
-bool sf_fast_supported(int ntypes);      // the pipelined kernel stages at most 64 atom types; beyond that the generic kernel runs
+bool sf_fast_supported(int ntypes);
+
+// structure factor of dense slices through a 1-D NUFFT along x (sf_nufft.cu): same output as launch_sf_fast.
+// sf_nufft_wanted: the grid is supported and the slices are dense enough for it to beat the direct sum (or the mode forces it)
+void sf_mode_set(int mode);      // 0 auto (default), 1 direct sum always, 2 NUFFT wherever supported
+int sf_mode();
+bool sf_nufft_supported(int ntypes, int nx, int ny);
+bool sf_nufft_wanted(int ntypes, int nx, int ny, int n_atoms, int nz);
+int launch_sf_nufft(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
+                    int ny, int pair_begin, int pair_count, int nf, const float* ff, float2* out, cudaStream_t s,
+                    cudaStream_t owner);
+void sf_nufft_release();      // the pipelined kernel stages at most 64 atom types; beyond that the generic kernel runs
 
 }  // namespace psb

@@ -1,0 +1,454 @@
+// Structure-factor sum of DENSE slices through a one-dimensional non-uniform FFT (reference: src/multislice/potentials.py
+// :319-330, the einsum over exp(-2 pi i kx x) exp(-2 pi i ky y) of the atoms of a slice, times the form factor).
+//
+// The direct sum (sf_fast.cu) costs 4 * atoms * (nx/2) * (ny/2) FMAs per slice pair: 0.65 GFMA at config C4 (1024 x 1024,
+// ~620 atoms per pair), 78 % of that configuration's potential build even at 59 % of the fp32 peak.  Here the x axis is
+// handled the NUFFT way (type 1, Dutt-Rokhlin / Barnett's "exponential of semicircle" kernel) and the y axis stays exact:
+//
+//     G[j, ky] = sum_a phi(M u_a - j) exp(-2 pi i ky y_a)          j = 0 .. M-1,  M = 2 nx fine cells, 8 taps per atom
+//     S[kx, ky] = f(kx, ky) / phi_hat(kx / M) * FFT_j(G)[kx, ky]    |kx| <= nx/2
+//
+// with phi(z) = exp(beta (sqrt(1 - (z/4)^2) - 1)), beta = 2.3 * 8: the aliasing error of this kernel at twofold
+// oversampling is ~1e-7 of the spectrum (measured against the direct sum: tests/test_gpu_parity.py), i.e. the float32
+// round-off of the sum itself.  Work per slice pair: atoms * 8 taps * ny complex FMAs + one 2 nx-point FFT per column and
+// atom type -- 8 x fewer flops than the direct sum at C4 and none of them atom-count dependent beyond the spreading.
+//
+//   K1  nufft_prep_kernel   one CTA per (slice pair, frame): orders the pair's atoms by (type, x bin of 16 fine cells) --
+//                           deterministically: ties keep list order -- and sums the (Nyquist, Nyquist) corner term.
+//   K2  nufft_cols_kernel   one CTA per (W adjacent ky columns, slice pair, frame): builds the G tile in shared memory
+//                           (thread (column, bin) spreads the atoms of its bin; even bins, then odd bins, so no two threads
+//                           touch a cell at the same time and the sums are reproducible), transforms it in place
+//                           (fast_fft.cuh: radix 16 x 8 x 16 for M = 2048, 16 x 4 x 16 for M = 1024), keeps the nx low
+//                           frequencies, divides out phi_hat, applies the form factor, accumulates over atom types and
+//                           writes the slice-pair spectrum S_2m + i S_2m+1 where the inverse transforms expect it.
+//
+// Hermitian part (the reference's Re(ifft2(.)), potentials.py:336-337): the ky Nyquist column is spread with cos(pi ny y)
+// instead of the complex phase, the kx Nyquist row is the mean of the +nx/2 and -nx/2 outputs of the fine transform, and
+// the corner gets the -sum sin sin term from K1 -- the same spectrum, entry for entry, as the direct kernels build.
+#include "fast_fft.cuh"
+#include "fast_path.h"
+#include "graph_cache.h"
+#include "pdl.cuh"
+#include "potential_kernels.cuh"
+#include "psb_rt.h"
+#include "tables.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace psb {
+
+namespace {
+
+using fast::cpx;
+
+constexpr int kTaps = 8;
+constexpr float kBeta = 2.30f * kTaps;
+constexpr int kMaxKeys = 8192;          // ntypes * bins the ordering kernel can histogram in shared memory
+
+std::atomic<int> g_sf_mode{0};          // 0 auto, 1 direct sum always, 2 NUFFT wherever it is supported
+
+struct NufftParams {
+    const int* offsets;         // (nf, nseg+1), first frame of the chunk
+    const unsigned int* ux;     // (nf, cap) fixed-point fractions, grouped by (slice, type) segment
+    const unsigned int* uy;
+    int cap, nz, ntypes, nx, ny;
+    int pair_begin, pair_count;
+    int nb, log_m;              // x bins per pair (= M / 16), log2(M)
+    // written by K1, read by K2
+    int* xoff;                  // (nf, pair_count, ntypes*nb + 1) offsets into the pair's record range, by (type, bin)
+    unsigned int* rx;           // (nf, cap) records of a pair, ordered by (type, bin), list order inside
+    unsigned int* ry;
+    unsigned int* rpar;         // 0: first slice of the pair (real part), 1: second (imaginary part)
+    float* corner;              // (nf, pair_count, ntypes, 2)  sum sin(pi nx u) sin(pi ny v) per type and slice of the pair
+    const float* ff;            // (ntypes, nx, ny) form factors
+    const float* dec;           // (nx) 1 / phi_hat(kx / M)
+    const float2* tw;           // staged twiddles of the M-point plan
+    float2* out;                // (nf, pair_count, nx, ny)
+};
+
+// ---- K1 ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nufft_prep_kernel(const NufftParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int* hist = reinterpret_cast<int*>(smem_raw);                      // [nkeys + 1]
+    const int nkeys = p.ntypes * p.nb;
+    unsigned short* keys = reinterpret_cast<unsigned short*>(hist + nkeys + 1 + 256);      // [kChunk]
+    int* part = hist + nkeys + 1;                                      // [256] scan partials
+    double* red = reinterpret_cast<double*>(smem_raw);                 // reduction scratch (reused after the ordering)
+    constexpr int kChunk = 4096;
+    const int t = threadIdx.x;
+    const int ml = blockIdx.x, f = blockIdx.y;
+    const int m = p.pair_begin + ml;
+    const int nseg = p.nz * p.ntypes;
+    const int* off = p.offsets + (long long)f * (nseg + 1);
+    const int s0 = 2 * m, s1 = (2 * m + 2 < p.nz) ? 2 * m + 2 : p.nz;
+    const int begin = off[s0 * p.ntypes], end = off[s1 * p.ntypes], n = end - begin;
+    const unsigned int* ux = p.ux + (long long)f * p.cap;
+    const unsigned int* uy = p.uy + (long long)f * p.cap;
+    const int shift = 32 - p.log_m + 4;                                // bin = fine cell / 16
+
+    auto seg_of = [&](int i) {                                         // list index -> segment (2 * ntypes candidates)
+        int seg = s0 * p.ntypes;
+        while (seg + 1 < s1 * p.ntypes && off[seg + 1] <= i) ++seg;
+        return seg;
+    };
+    auto key_of = [&](int i, int* par) {
+        const int seg = seg_of(i);
+        *par = seg / p.ntypes - s0;
+        return (seg % p.ntypes) * p.nb + (int)(ux[i] >> shift);
+    };
+
+    for (int k = t; k <= nkeys; k += 256) hist[k] = 0;
+    __syncthreads();
+    for (int i = begin + t; i < end; i += 256) {
+        int par;
+        atomicAdd(&hist[key_of(i, &par) + 1], 1);                      // integer counts: order-independent
+    }
+    __syncthreads();
+    // exclusive scan of hist[1..nkeys] in place (hist[k] = atoms with a smaller key)
+    {
+        const int chunk = (nkeys + 255) / 256;
+        const int i0 = 1 + t * chunk, i1 = (i0 + chunk < nkeys + 1) ? i0 + chunk : nkeys + 1;
+        int s = 0;
+        for (int i = i0; i < i1; ++i) s += hist[i];
+        part[t] = s;
+        __syncthreads();
+        int base = 0;
+        for (int k = 0; k < t; ++k) base += part[k];
+        for (int i = i0; i < i1; ++i) {
+            base += hist[i];
+            hist[i] = base;
+        }
+        __syncthreads();
+    }
+    int* xoff = p.xoff + ((long long)f * p.pair_count + ml) * (nkeys + 1);
+    for (int k = t; k <= nkeys; k += 256) xoff[k] = hist[k];
+    // position of atom i = hist[key] + number of earlier list entries with the same key (stable, hence reproducible)
+    unsigned int* rx = p.rx + (long long)f * p.cap + begin;
+    unsigned int* ry = p.ry + (long long)f * p.cap + begin;
+    unsigned int* rpar = p.rpar + (long long)f * p.cap + begin;
+    for (int a0 = 0; a0 < n; a0 += 256) {
+        const int i = a0 + t;
+        int par = 0, same = 0;
+        const int key = i < n ? key_of(begin + i, &par) : -1;
+        for (int c0 = 0; c0 < a0 + 256 && c0 < n; c0 += kChunk) {
+            const int mchunk = n - c0 < kChunk ? n - c0 : kChunk;
+            __syncthreads();
+            for (int k = t; k < mchunk; k += 256) {
+                int pk;
+                keys[k] = (unsigned short)key_of(begin + c0 + k, &pk);
+            }
+            __syncthreads();
+            const int lim = (i - c0) < mchunk ? (i - c0) : mchunk;       // entries of this chunk that precede i
+            for (int k = 0; k < lim; ++k) same += keys[k] == key;
+        }
+        if (i < n) {
+            const int pos = hist[key] + same;
+            rx[pos] = ux[begin + i];
+            ry[pos] = uy[begin + i];
+            rpar[pos] = (unsigned int)par;
+        }
+    }
+    // corner term per (type, slice of the pair): sum sin(pi nx u) sin(pi ny v), fixed summation order
+    __syncthreads();
+    for (int c = 0; c < 2 * p.ntypes; ++c) {
+        const int typ = c >> 1, par = c & 1;
+        const int seg = (s0 + par) * p.ntypes + typ;
+        double acc = 0.0;
+        if (s0 + par < p.nz)
+            for (int i = off[seg] + t; i < off[seg + 1]; i += 256) {
+                const float2 ex = unit_phase(p.nx / 2, ux[i]), ey = unit_phase(p.ny / 2, uy[i]);     // (cos, -sin)(pi n u)
+                acc += (double)(ex.y * ey.y);
+            }
+        red[t] = acc;
+        __syncthreads();
+        for (int h = 128; h > 0; h >>= 1) {
+            if (t < h) red[t] += red[t + h];
+            __syncthreads();
+        }
+        if (t == 0) p.corner[(((long long)f * p.pair_count + ml) * p.ntypes + typ) * 2 + par] = (float)red[0];
+        __syncthreads();
+    }
+}
+
+// ---- K2 ------------------------------------------------------------------------------------------------------
+template <int M>
+struct NufftCfg {
+    static constexpr int T = M / 16;                 // threads per column = x bins per pair
+    static constexpr int kThreads = 512;
+    static constexpr int W = kThreads / T;           // columns per tile: 4 (M = 2048), 8 (M = 1024)
+    static constexpr int kRows = M + M / 16;         // padded
+    static constexpr size_t kSmem = (size_t)kRows * W * sizeof(float2);
+    static constexpr int kLogM = M == 2048 ? 11 : 10;
+};
+
+template <int M>
+struct NufftXchg {
+    cpx* t;
+    int c;
+    __device__ __forceinline__ cpx* buf(int) const { return t; }
+    __device__ __forceinline__ int at(int q) const { return (q + (q >> 4)) * NufftCfg<M>::W + c; }
+    __device__ __forceinline__ void after_store(int) const { __syncthreads(); }
+    __device__ __forceinline__ void after_load(int) const { __syncthreads(); }
+    __device__ __forceinline__ void mid_sync(int) const { __syncthreads(); }
+};
+
+__device__ __forceinline__ float es_weight(float z) {           // phi(z), |z| <= 4
+    const float s = fmaxf(1.0f - z * z * (1.0f / 16.0f), 0.0f);
+    return expf(kBeta * (sqrtf(s) - 1.0f));
+}
+
+template <int M>
+__global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(const NufftParams p) {
+    using C = NufftCfg<M>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* tile = reinterpret_cast<float2*>(smem_raw);
+    const int tid = threadIdx.x, c = tid % C::W, j = tid / C::W;
+    const int my = blockIdx.x * C::W + c;                        // column, fft order
+    const int ml = blockIdx.y, f = blockIdx.z;
+    const int nx = M / 2;
+    fast::Twiddles<M> tw;
+    tw.load(p.tw, j);
+    const NufftXchg<M> xc{reinterpret_cast<cpx*>(tile), c};
+    const int msy = my < (p.ny + 1) / 2 ? my : my - p.ny;
+    const bool nyq_y = (p.ny % 2 == 0) && my == p.ny / 2;
+    const int nkeys = p.ntypes * C::T;
+    const int* xoff = p.xoff + ((long long)f * p.pair_count + ml) * (nkeys + 1);
+    const int m = p.pair_begin + ml;
+    const int nseg = p.nz * p.ntypes;
+    const long long rbase = (long long)f * p.cap + p.offsets[(long long)f * (nseg + 1) + 2 * m * p.ntypes];
+    const unsigned int* rx = p.rx + rbase;
+    const unsigned int* ry = p.ry + rbase;
+    const unsigned int* rpar = p.rpar + rbase;
+    const float* corner = p.corner + ((long long)f * p.pair_count + ml) * p.ntypes * 2;
+    constexpr unsigned int kFracBits = 32 - C::kLogM;
+    constexpr float kFracScale = 1.0f / (float)(1u << kFracBits);
+
+    cpx acc_out[8];
+#pragma unroll
+    for (int s = 0; s < 8; ++s) acc_out[s] = fast::c_make(0.f, 0.f);
+
+    for (int z = 0; z < p.ntypes; ++z) {
+        // ---- spread the atoms of type z into the tile: rows = fine cells, this thread's column
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) tile[xc.at(16 * j + rr)] = make_float2(0.f, 0.f);
+        __syncthreads();
+        for (int phase = 0; phase < 2; ++phase) {
+            if ((j & 1) == phase) {
+                const int i0 = xoff[z * C::T + j], i1 = xoff[z * C::T + j + 1];
+                for (int i = i0; i < i1; ++i) {
+                    const unsigned int u = rx[i], v = ry[i];
+                    float2 e;
+                    if (nyq_y) e = make_float2(unit_phase(p.ny / 2, v).x, 0.f);       // cos(pi ny v): the Hermitian part
+                    else e = unit_phase(msy, v);
+                    if (rpar[i]) e = make_float2(-e.y, e.x);                            // second slice of the pair: times i
+                    const int cell = (int)(u >> kFracBits);
+                    const float fr = (float)(u & ((1u << kFracBits) - 1u)) * kFracScale;
+#pragma unroll
+                    for (int k = 0; k < kTaps; ++k) {
+                        const int row = (cell - 3 + k) & (M - 1);
+                        const float w = es_weight((float)(k - 3) - fr);
+                        const int idx = xc.at(row);
+                        float2 g = tile[idx];
+                        g.x = fmaf(w, e.x, g.x);
+                        g.y = fmaf(w, e.y, g.y);
+                        tile[idx] = g;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // ---- M-point transform along x, in place in the tile
+        cpx v16[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v16[e] = reinterpret_cast<const cpx*>(tile)[xc.at(j + e * C::T)];
+        __syncthreads();
+        const float* ffz = p.ff + ((long long)z * nx) * p.ny + my;
+        cpx nyq_hold = fast::c_make(0.f, 0.f);
+        fast::line_fft<M, -1>(
+            [&](int e) { return v16[e]; },
+            [&](int t, cpx a) {
+                // fine frequency j + T*t; kept: t in {0..3} (kx >= 0) and {12..15} (kx < 0), coarse row kxi = j + T*s
+                if (t >= 4 && t < 12) {
+                    if (t == 4) nyq_hold = a;                    // +nx/2 (j == 0 only)
+                    return;
+                }
+                const int s = t < 4 ? t : t - 8;
+                const int kxi = j + C::T * s;
+                if (s == 4 && j == 0) {                          // kx Nyquist row: mean of the +nx/2 and -nx/2 outputs
+                    a = fast::mul2(fast::add2(a, nyq_hold), fast::c_make(0.5f, 0.5f));
+                    if (nyq_y)                                    // corner: cos cos - sin sin
+                        a = fast::sub2(a, fast::c_make(corner[2 * z] / p.dec[kxi], corner[2 * z + 1] / p.dec[kxi]));
+                }
+                const float g = ffz[(long long)kxi * p.ny] * p.dec[kxi];
+                acc_out[s < 8 ? s : 0] = fast::fma2(a, fast::c_make(g, g), acc_out[s < 8 ? s : 0]);
+            },
+            tw, j, xc, 0);
+    }
+    float2* out = p.out + (((long long)f * p.pair_count + ml) * nx) * p.ny + my;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) {
+        const int kxi = j + C::T * s;
+        out[(long long)kxi * p.ny] = make_float2(fast::c_re(acc_out[s]), fast::c_im(acc_out[s]));
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------
+struct NufftWorkspace {
+    void* block = nullptr;
+    size_t bytes = 0;
+};
+std::mutex g_mu;
+std::map<std::pair<int, cudaStream_t>, NufftWorkspace> g_ws;      // (device, owner stream)
+std::map<std::pair<int, int>, float*> g_dec;                       // (device, nx) -> 1 / phi_hat
+
+// phi_hat(xi) = integral_{-4}^{4} phi(z) cos(2 pi xi z) dz, composite Simpson (phi is smooth inside, ~1e-8 at the ends)
+double phi_hat(double xi) {
+    const int n = 4096;
+    const double a = -0.5 * kTaps, h = (double)kTaps / n, pi = 3.14159265358979323846;
+    auto fn = [&](double z) {
+        const double s = 1.0 - z * z / 16.0;
+        return std::exp((double)kBeta * (std::sqrt(s > 0 ? s : 0) - 1.0)) * std::cos(2.0 * pi * xi * z);
+    };
+    double acc = fn(a) + fn(a + n * h);
+    for (int i = 1; i < n; ++i) acc += fn(a + i * h) * ((i & 1) ? 4.0 : 2.0);
+    return acc * h / 3.0;
+}
+
+int dec_table(int nx, const float** out, cudaStream_t s) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const auto key = std::make_pair(rt::device(), nx);
+    auto it = g_dec.find(key);
+    if (it != g_dec.end()) {
+        *out = it->second;
+        return PSB_OK;
+    }
+    std::vector<float> host(nx);
+    const int M = 2 * nx;
+    for (int i = 0; i < nx; ++i) {
+        const int mfreq = i < (nx + 1) / 2 ? i : i - nx;
+        host[i] = (float)(1.0 / phi_hat((double)mfreq / (double)M));
+    }
+    float* d = static_cast<float*>(rt::dev_alloc(nx * sizeof(float)));
+    if (!d) return PSB_ERR_NOMEM;
+    int rc = rt::h2d(d, host.data(), nx * sizeof(float), s);
+    if (rc != PSB_OK) return rc;
+    g_dec[key] = d;
+    *out = d;
+    return PSB_OK;
+}
+
+template <int M>
+int cols_go(const NufftParams& p, int nf, cudaStream_t s) {
+    using C = NufftCfg<M>;
+    static rt::PerDeviceOnce once;
+    int rc0 = once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(nufft_cols_kernel<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem);
+        if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("nufft columns: ") + cudaGetErrorString(e));
+        return (int)PSB_OK;
+    });
+    if (rc0 != PSB_OK) return rc0;
+    nufft_cols_kernel<M><<<dim3(p.ny / C::W, p.pair_count, nf), C::kThreads, C::kSmem, s>>>(p);
+    ++launch_counter();
+    return rt::check("nufft columns launch");
+}
+
+}  // namespace
+
+void sf_mode_set(int mode) { g_sf_mode.store(mode < 0 ? 0 : (mode > 2 ? 2 : mode)); }
+int sf_mode() { return g_sf_mode.load(); }
+
+bool sf_nufft_supported(int ntypes, int nx, int ny) {
+    if (nx != 512 && nx != 1024) return false;
+    const int W = nx == 1024 ? 4 : 8;
+    return ny % W == 0 && ntypes * (nx / 8) <= kMaxKeys;
+}
+
+// dense enough for the transform to beat the direct sum: atoms per slice pair and type (measured crossover)
+bool sf_nufft_wanted(int ntypes, int nx, int ny, int n_atoms, int nz) {
+    const int mode = g_sf_mode.load();
+    if (mode == 1 || !sf_nufft_supported(ntypes, nx, ny)) return false;
+    if (mode == 2) return true;
+    const double per_pair_type = 2.0 * (double)n_atoms / (double)(nz > 0 ? nz : 1) / (double)ntypes;
+    return nx >= 1024 && per_pair_type >= 200.0;
+}
+
+void sf_nufft_release() {
+    std::lock_guard<std::mutex> lk(g_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : g_ws) {
+        cudaSetDevice(kv.first.first);
+        rt::dev_free(kv.second.block);
+    }
+    for (auto& kv : g_dec) {
+        cudaSetDevice(kv.first.first);
+        rt::dev_free(kv.second);
+    }
+    cudaSetDevice(cur);
+    g_ws.clear();
+    g_dec.clear();
+}
+
+int launch_sf_nufft(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
+                    int ny, int pair_begin, int pair_count, int nf, const float* ff, float2* out, cudaStream_t s,
+                    cudaStream_t owner) {
+    if (!sf_nufft_supported(ntypes, nx, ny)) return fail(PSB_ERR_UNSUPPORTED, "nufft structure factor: unsupported grid");
+    const int M = 2 * nx;
+    NufftParams p;
+    std::memset(&p, 0, sizeof(p));
+    p.offsets = offsets; p.ux = ux; p.uy = uy; p.cap = cap; p.nz = nz; p.ntypes = ntypes; p.nx = nx; p.ny = ny;
+    p.pair_begin = pair_begin; p.pair_count = pair_count; p.nb = M / 16; p.log_m = M == 2048 ? 11 : 10;
+    p.ff = ff; p.out = out;
+    int rc = dec_table(nx, &p.dec, owner);
+    if (rc != PSB_OK) return rc;
+    FftTables tb;
+    int N = 0;
+    bool blue = false;
+    rc = get_fft_tables(M, &tb, &N, &blue, owner);
+    if (rc != PSB_OK) return rc;
+    if (blue || N != M) return fail(PSB_ERR_UNSUPPORTED, "nufft structure factor: power-of-two fine grid expected");
+    p.tw = tb.tw;
+    const int nkeys = ntypes * p.nb;
+    const size_t n_xoff = (size_t)nf * pair_count * (nkeys + 1), n_rec = (size_t)nf * cap, n_corner = (size_t)nf * pair_count * ntypes * 2;
+    const size_t need = n_xoff * sizeof(int) + 3 * n_rec * sizeof(unsigned int) + n_corner * sizeof(float) + 256;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        NufftWorkspace& w = g_ws[std::make_pair(rt::device(), owner)];
+        if (need > w.bytes) {
+            cudaError_t e = cudaStreamSynchronize(owner);      // kernels of earlier chunks may still read the old block
+            if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("nufft workspace sync: ") + cudaGetErrorString(e));
+            graph_cache_release();                             // recorded launch sequences point at the block freed here
+            rt::dev_free(w.block);
+            w.block = rt::dev_alloc(need);
+            w.bytes = w.block ? need : 0;
+            if (!w.block) return PSB_ERR_NOMEM;
+        }
+        p.xoff = reinterpret_cast<int*>(w.block);
+        p.rx = reinterpret_cast<unsigned int*>(p.xoff + n_xoff);
+        p.ry = p.rx + n_rec;
+        p.rpar = p.ry + n_rec;
+        p.corner = reinterpret_cast<float*>(p.rpar + n_rec);
+    }
+    const size_t prep_smem = (size_t)(nkeys + 1 + 256) * sizeof(int) + 4096 * sizeof(unsigned short) + 16;
+    const size_t prep_smem2 = prep_smem < 256 * sizeof(double) ? 256 * sizeof(double) : prep_smem;
+    static rt::PerDeviceOnce once;
+    rc = once.run([] {
+        cudaError_t e = cudaFuncSetAttribute(nufft_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("nufft prep: ") + cudaGetErrorString(e));
+        return (int)PSB_OK;
+    });
+    if (rc != PSB_OK) return rc;
+    nufft_prep_kernel<<<dim3(pair_count, nf), 256, prep_smem2, s>>>(p);
+    ++launch_counter();
+    rc = rt::check("nufft prep launch");
+    if (rc != PSB_OK) return rc;
+    return M == 2048 ? cols_go<2048>(p, nf, s) : cols_go<1024>(p, nf, s);
+}
+
+}  // namespace psb

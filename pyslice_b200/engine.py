@@ -27,6 +27,11 @@ T_BATCH_BYTES = 48 << 30
 SCRATCH_BYTES = 64 << 20
 
 
+# per-device batch workspaces of the calculators (multislice/calculators.py: run()), kept so that consecutive runs and
+# consecutive calculators of one geometry see the same device addresses (CUDA-graph replay in libpsb keys on them)
+WORKSPACES = {}
+
+
 class PhaseTimer:
     """Optional CUDA-event timing of the pipeline phases on the launching stream (used by bench.py to
     report the slice-step kernel's own duration).  `with timer.phase("propagate"): ...` records an
@@ -85,6 +90,12 @@ def set_fast_path(enable) -> None:
     True / 1 = fused persistent kernels (default), False / 0 = generic line-pass kernels."""
     level = 1 if enable is True else (0 if enable is False else int(enable))
     _lib.lib().psb_set_fast_path(level)
+
+
+def set_sf_mode(mode: int) -> None:
+    """Structure-factor algorithm of the potential build: 0 automatic (default), 1 direct sum always, 2 the 1-D NUFFT of
+    csrc/sf_nufft.cu wherever it is implemented (A/B tests and microbenchmarks)."""
+    _lib.lib().psb_set_sf_mode(int(mode))
 
 
 def set_graph_mode(on: bool) -> None:

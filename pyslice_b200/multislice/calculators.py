@@ -227,8 +227,8 @@ class MultisliceCalculator:
 
     def release_workspace(self) -> None:
         """drop the per-batch device buffers kept between run() calls (the transmission stack of one frame batch, psi work
-        area, binning scratch)"""
-        self._workspace = None
+        area, binning scratch) of this calculator's device"""
+        engine.WORKSPACES.pop(str(self.device), None)
 
     def _cache_file(self, frame: int) -> Path:
         return self.output_dir / f"frame_{frame}.npy"
@@ -251,20 +251,22 @@ class MultisliceCalculator:
         # one probe per frame: the stack is written once and read once, so it is kept as float32 phases (half the HBM
         # traffic, exp(i*phase) evaluated inside the fused slice step); shared by several probes it stays complex64
         use_phase = P == 1 and engine.phase_format_supported(plan)
-        # Per-batch workspaces live on the calculator and are reused by every batch and every later run(): besides saving
-        # the allocations, stable addresses let libpsb replay a batch's ~2000 launches as recorded CUDA graphs
-        # (graph_cache.cu).  release_workspace() frees them.
+        # Per-batch workspaces are reused by every batch, every later run() and the next calculator of the same geometry on
+        # this device (one set per device is kept, see engine.WORKSPACES): besides saving the allocations, stable addresses
+        # let libpsb replay a batch's ~2000 launches as recorded CUDA graphs (graph_cache.cu).  release_workspace() frees them.
         A = int(self.trajectory.positions.shape[1])
-        ws_key = (fb, pb, P, nx, ny, plan.nz, use_phase, A)
-        ws = getattr(self, "_workspace", None)
+        ws_key = (str(self.device), fb, pb, P, nx, ny, plan.nz, use_phase, A)
+        ws = engine.WORKSPACES.get(str(self.device))
         if ws is None or ws["key"] != ws_key:
+            engine.WORKSPACES.pop(str(self.device), None)
+            ws = None
             ws = dict(key=ws_key,
                       tbuf=torch.empty((fb, plan.nz, nx, ny), dtype=torch.float32 if use_phase else torch.complex64, device=self.device),
                       work=torch.empty((fb * min(pb, P), nx, ny), dtype=torch.complex64, device=self.device),
                       t0=torch.empty((fb, nx, ny), dtype=torch.complex64, device=self.device) if use_phase else None,
                       scratch=torch.empty((nx * ny * engine.chunk_images(plan, fb),), dtype=torch.complex64, device=self.device),
                       bins=engine.bin_buffers(plan, fb, A))
-            self._workspace = ws
+            engine.WORKSPACES[str(self.device)] = ws
         tbuf, work = ws["tbuf"], ws["work"]
         # the result store is allocated AFTER the multi-GB stack: while a previous result is still alive the caching
         # allocator would otherwise carve the new store out of the cached stack block and then cudaMalloc a fresh stack

@@ -38,11 +38,16 @@ std::vector<float2> staged_table() {
         for (int k = 0; k < 16; ++k) t.push_back(w(k, 32));
         for (int tt = 1; tt < 16; ++tt)
             for (int k = 0; k < 32; ++k) t.push_back(w((long long)k * tt, 512));
-    } else {
+    } else if (N == 1024) {
         for (int tt = 1; tt < 4; ++tt)
             for (int k = 0; k < 16; ++k) t.push_back(w((long long)k * tt, 64));
         for (int tt = 1; tt < 16; ++tt)
             for (int k = 0; k < 64; ++k) t.push_back(w((long long)k * tt, 1024));
+    } else {
+        for (int tt = 1; tt < 8; ++tt)
+            for (int k = 0; k < 16; ++k) t.push_back(w((long long)k * tt, 128));
+        for (int tt = 1; tt < 16; ++tt)
+            for (int k = 0; k < 128; ++k) t.push_back(w((long long)k * tt, 2048));
     }
     return t;
 }
@@ -82,6 +87,8 @@ extern "C" int fast_fft_line(int N, int dir, const float* in, float* out, int re
     else if (N == 512) run_line<512, +1>(i2, o2, reps);
     else if (N == 1024 && dir < 0) run_line<1024, -1>(i2, o2, reps);
     else if (N == 1024) run_line<1024, +1>(i2, o2, reps);
+    else if (N == 2048 && dir < 0) run_line<2048, -1>(i2, o2, reps);
+    else if (N == 2048) run_line<2048, +1>(i2, o2, reps);
     else return -1;
     return 0;
 }

@@ -23,7 +23,7 @@ def harness():
     return lib
 
 
-@pytest.mark.parametrize("N", [256, 512, 1024])
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048])
 @pytest.mark.parametrize("direction", [-1, 1])
 def test_line_fft_matches_numpy(harness, N, direction):
     rng = np.random.default_rng(N + direction)
@@ -41,7 +41,7 @@ def test_line_fft_matches_numpy(harness, N, direction):
     assert np.abs(out - want).max() < 5e-7
 
 
-@pytest.mark.parametrize("N", [256, 512, 1024])
+@pytest.mark.parametrize("N", [256, 512, 1024, 2048])
 def test_back_to_back_transforms_share_exchange_buffers(harness, N):
     """two transforms in a row (as in a tile: FFT a, multiply, FFT b) reuse the alternating buffers safely"""
     rng = np.random.default_rng(3)

@@ -605,3 +605,41 @@ def test_graph_replay_is_bit_identical_and_survives_workspace_growth():
     runs(other, 3)
     for g in runs(calc, 3):                  # the small job again, through graphs recorded afresh
         assert torch.equal(g, want)
+
+
+@pytest.mark.parametrize("box,n_atoms,types,n_frames", [
+    ((102.35, 102.35, 1.7), 6000, (14,), 2),          # 1024 x 1024, 3 slices (last pair half empty), ~4000 atoms per pair
+    ((102.35, 25.55, 1.2), 2500, (6, 14), 2),         # 1024 x 256, two types
+    ((51.15, 51.15, 2.2), 3000, (5, 6, 7), 2),        # 512 x 512 (1024-point fine grid), three types
+    ((51.15, 102.35, 0.7), 1500, (14,), 1),           # 512 x 1024, one slice pair
+])
+def test_potential_nufft_vs_direct_sum_and_oracle(box, n_atoms, types, n_frames):
+    """Structure factor of dense slices through the 1-D NUFFT along x (sf_nufft.cu: ES-kernel spreading onto a twofold
+    oversampled grid in shared memory, fused 2 nx-point transform, deconvolution) against the direct sum (sf_fast.cu) on
+    the same inputs -- atoms on slice bounds and outside the box included -- and against the oracle's potential."""
+    from pyslice_b200 import engine, hostmath, synthetic
+    traj = synthetic.random_trajectory(n_atoms=n_atoms, box=box, n_frames=n_frames, seed=29, types=types, stray=True)
+    xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
+    plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
+    pos = dev(traj.positions)
+    out = {}
+    try:
+        for mode in (2, 1):
+            engine.set_sf_mode(mode)
+            t, V = engine.build_transmission(plan, pos, want_potential=True)
+            out[mode] = (t.clone(), V.clone())
+        engine.set_sf_mode(2)
+        t2, V2 = engine.build_transmission(plan, pos, want_potential=True)
+        assert torch.equal(V2, out[2][1]) and torch.equal(t2, out[2][0])          # reproducible bit for bit
+        ph = engine.build_transmission(plan, pos, phase=True)
+        assert rel_l2(ph.cpu().numpy(), (plan.sigma * out[2][1]).cpu().numpy()) < 1e-6
+    finally:
+        engine.set_sf_mode(0)
+    err = rel_l2(out[2][1].cpu().numpy(), out[1][1].cpu().numpy())
+    print(f"NUFFT vs direct sum, potential rel-L2: {err:.3e}")
+    assert err < 3e-6
+    Vref = orc.potential(xs, ys, zs, traj.positions[0], traj.atom_types, workers=8)      # (nx, ny, nz)
+    for mode in (2, 1):
+        e = rel_l2(np.moveaxis(out[mode][1][0].cpu().numpy(), 0, 2), Vref)
+        print(f"potential rel-L2 vs oracle, sf mode {mode}: {e:.3e}")
+        assert e < 1e-5, mode

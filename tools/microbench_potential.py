@@ -18,18 +18,21 @@ xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
 plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
 pos = torch.from_numpy(traj.positions).cuda()
 PHASE = os.environ.get("PSB_PHASE") == "1"      # stack as float32 phases (single-probe format)
-tbuf = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.float32 if PHASE else torch.complex64, device="cuda")
+engine.set_sf_mode(int(os.environ.get("PSB_SF_MODE", "0")))      # 0 auto, 1 direct sum, 2 NUFFT along x
+print("sf mode", os.environ.get("PSB_SF_MODE", "0"))
+tbuf = torch.empty((F, plan.nz, plan.nx, plan.ny), dtype=torch.complex64, device="cuda")      # large enough for either format
+tphase = tbuf.view(torch.float32).reshape(-1)[:tbuf.numel()].view(F, plan.nz, plan.nx, plan.ny)
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for fast in [int(x) for x in os.environ.get('PSB_LEVELS', '2,1,0').split(',')]:
     engine.set_fast_path(fast)
     for mb in sizes:
         engine.SCRATCH_BYTES = mb << 20
         for _ in range(2):
-            engine.build_transmission(plan, pos, out=tbuf, phase=PHASE and fast > 0)
+            engine.build_transmission(plan, pos, out=tphase if PHASE and fast > 0 else tbuf, phase=PHASE and fast > 0)
         torch.cuda.synchronize()
         a.record()
         for _ in range(3):
-            engine.build_transmission(plan, pos, out=tbuf, phase=PHASE and fast > 0)
+            engine.build_transmission(plan, pos, out=tphase if PHASE and fast > 0 else tbuf, phase=PHASE and fast > 0)
         b.record(); torch.cuda.synchronize()
         ms = a.elapsed_time(b) / 3
         print(f"{'level %d' % fast} scratch {mb:4d} MB  F={F}: {ms:8.3f} ms  {1e3*ms/(F*plan.nz):6.3f} us per slice  "
