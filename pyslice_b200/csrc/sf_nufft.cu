@@ -183,7 +183,9 @@ struct NufftCfg {
     static constexpr int kThreads = 512;
     static constexpr int W = kThreads / T;           // columns per tile: 4 (M = 2048), 8 (M = 1024)
     static constexpr int kRows = M + M / 16;         // padded
-    static constexpr size_t kSmem = (size_t)kRows * W * sizeof(float2);
+    static constexpr size_t kTileBytes = (size_t)kRows * W * sizeof(float2);
+    static constexpr int kStage = 1536;              // records of one atom type staged in shared memory (more: read from L2)
+    static constexpr size_t kSmem = kTileBytes + 3 * kStage * sizeof(unsigned int) + (T + 1) * sizeof(int);
     static constexpr int kLogM = M == 2048 ? 11 : 10;
 };
 
@@ -198,9 +200,30 @@ struct NufftXchg {
     __device__ __forceinline__ void mid_sync(int) const { __syncthreads(); }
 };
 
-__device__ __forceinline__ float es_weight(float z) {           // phi(z), |z| <= 4
-    const float s = fmaxf(1.0f - z * z * (1.0f / 16.0f), 0.0f);
-    return expf(kBeta * (sqrtf(s) - 1.0f));
+// phi(z) = exp(beta (sqrt(1 - z^2/16) - 1)), |z| <= 4, through the SFU with one correction step each (relative error
+// ~2e-7; the library sqrtf / expf cost 5 x the instructions, and a tile evaluates ~40 000 weights)
+__device__ __forceinline__ float es_weight(float z) {
+    const float s = fmaxf(fmaf(-z * z, 1.0f / 16.0f, 1.0f), 1e-30f);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    float q = s * r;                                             // ~sqrt(s)
+    q = fmaf(0.5f * r, fmaf(-q, q, s), q);                       // one Newton step
+    const float x = kBeta * (q - 1.0f);                          // in [-beta, 0]
+    const float kL2e = 1.4426950408889634f, kL2eLo = 1.925963033500e-8f;
+    const float t = x * kL2e;
+    const float rem = fmaf(x, kL2e, -t) + x * kL2eLo;            // what the rounding of t lost, in units of log2
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return fmaf(e, rem * 0.6931471805599453f, e);
+}
+
+// exp(-2*pi*i*m*v) with v a 32-bit turn fraction: exact integer phase reduction, then the SFU on an angle in [-pi, pi)
+// (absolute error ~4e-7, the accuracy of the direct kernels' phase tables, sf_fast.cu)
+__device__ __forceinline__ float2 unit_phase_fast(int m, unsigned int v) {
+    const int ph = (int)((unsigned int)m * v);
+    float sn, cs;
+    __sincosf((float)ph * (3.14159265358979323846f * 4.656612873077393e-10f), &sn, &cs);
+    return make_float2(cs, -sn);
 }
 
 template <int M>
@@ -208,6 +231,10 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     using C = NufftCfg<M>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tile = reinterpret_cast<float2*>(smem_raw);
+    unsigned int* s_rx = reinterpret_cast<unsigned int*>(smem_raw + C::kTileBytes);      // [kStage] records of the current type
+    unsigned int* s_ry = s_rx + C::kStage;
+    unsigned int* s_rp = s_ry + C::kStage;
+    int* s_xoff = reinterpret_cast<int*>(s_rp + C::kStage);                              // [T + 1]
     const int tid = threadIdx.x, c = tid % C::W, j = tid / C::W;
     const int my = blockIdx.x * C::W + c;                        // column, fft order
     const int ml = blockIdx.y, f = blockIdx.z;
@@ -228,36 +255,66 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     const float* corner = p.corner + ((long long)f * p.pair_count + ml) * p.ntypes * 2;
     constexpr unsigned int kFracBits = 32 - C::kLogM;
     constexpr float kFracScale = 1.0f / (float)(1u << kFracBits);
+    // Spreading runs in its own thread -> (column, bin) map: a warp holds bins of ONE parity (its W lanes per bin are the
+    // W columns of the tile), so the even-bin phase occupies the even warps only and the odd warps wait at the barrier
+    // instead of issuing predicated-off instructions.  The W lanes of a bin share the atom: each evaluates 8 / W of its
+    // tap weights and the group exchanges them by shuffle.
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int kBinsPerWarp = 32 / C::W;
+    constexpr int kWeightsPerLane = kTaps / C::W;                 // 2 (W = 4) or 1 (W = 8)
+    const int sbin = 2 * (kBinsPerWarp * (warp >> 1) + lane / C::W) + (warp & 1);
+    const int group0 = lane & ~(C::W - 1);
 
     cpx acc_out[8];
 #pragma unroll
     for (int s = 0; s < 8; ++s) acc_out[s] = fast::c_make(0.f, 0.f);
 
     for (int z = 0; z < p.ntypes; ++z) {
-        // ---- spread the atoms of type z into the tile: rows = fine cells, this thread's column
+        // ---- stage this type's records and bin offsets, clear the tile
+        const int r0 = xoff[z * C::T], r1 = xoff[(z + 1) * C::T];
+        const int nstage = (r1 - r0) < C::kStage ? (r1 - r0) : C::kStage;
+        for (int i = tid; i < nstage; i += C::kThreads) {
+            s_rx[i] = rx[r0 + i];
+            s_ry[i] = ry[r0 + i];
+            s_rp[i] = rpar[r0 + i];
+        }
+        for (int i = tid; i <= C::T; i += C::kThreads) s_xoff[i] = xoff[z * C::T + i] - r0;
 #pragma unroll
         for (int rr = 0; rr < 16; ++rr) tile[xc.at(16 * j + rr)] = make_float2(0.f, 0.f);
         __syncthreads();
+        // ---- spread: rows = fine cells, this lane's column
         for (int phase = 0; phase < 2; ++phase) {
-            if ((j & 1) == phase) {
-                const int i0 = xoff[z * C::T + j], i1 = xoff[z * C::T + j + 1];
-                for (int i = i0; i < i1; ++i) {
-                    const unsigned int u = rx[i], v = ry[i];
-                    float2 e;
-                    if (nyq_y) e = make_float2(unit_phase(p.ny / 2, v).x, 0.f);       // cos(pi ny v): the Hermitian part
-                    else e = unit_phase(msy, v);
-                    if (rpar[i]) e = make_float2(-e.y, e.x);                            // second slice of the pair: times i
+            if ((warp & 1) == phase) {
+                const int i0 = s_xoff[sbin], i1 = s_xoff[sbin + 1];
+                int trips = i1 - i0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));
+                for (int it = 0; it < trips; ++it) {
+                    const int i = i0 + it;
+                    const bool live = i < i1;
+                    unsigned int u = 0, v = 0, par = 0;
+                    if (live) {
+                        if (i < C::kStage) { u = s_rx[i]; v = s_ry[i]; par = s_rp[i]; }
+                        else { u = rx[r0 + i]; v = ry[r0 + i]; par = rpar[r0 + i]; }
+                    }
+                    float2 e = nyq_y ? make_float2(unit_phase_fast(p.ny / 2, v).x, 0.f)      // cos(pi ny v): the Hermitian part
+                                     : unit_phase_fast(msy, v);
+                    if (par) e = make_float2(-e.y, e.x);                                      // second slice of the pair: times i
                     const int cell = (int)(u >> kFracBits);
                     const float fr = (float)(u & ((1u << kFracBits) - 1u)) * kFracScale;
+                    float wl[kWeightsPerLane];
+#pragma unroll
+                    for (int q = 0; q < kWeightsPerLane; ++q) wl[q] = es_weight((float)(c * kWeightsPerLane + q - 3) - fr);
 #pragma unroll
                     for (int k = 0; k < kTaps; ++k) {
-                        const int row = (cell - 3 + k) & (M - 1);
-                        const float w = es_weight((float)(k - 3) - fr);
-                        const int idx = xc.at(row);
-                        float2 g = tile[idx];
-                        g.x = fmaf(w, e.x, g.x);
-                        g.y = fmaf(w, e.y, g.y);
-                        tile[idx] = g;
+                        const float w = __shfl_sync(0xffffffffu, wl[k % kWeightsPerLane], group0 + k / kWeightsPerLane);
+                        if (live) {
+                            const int idx = xc.at((cell - 3 + k) & (M - 1));
+                            float2 g = tile[idx];
+                            g.x = fmaf(w, e.x, g.x);
+                            g.y = fmaf(w, e.y, g.y);
+                            tile[idx] = g;
+                        }
                     }
                 }
             }
