@@ -177,6 +177,10 @@ static int build_eager(const int32_t* offsets, const uint32_t* ux, const uint32_
         int rc0 = sf_fast_prepare(formfactors, ntypes, nx, ny, s, owner);
         if (rc0 != PSB_OK) return rc0;
     }
+    if (sf_nufft) {
+        int rc0 = sf_nufft_prepare(offsets, ux, uy, 2 * n_atoms, nz, ntypes, nx, ny, n_frames, formfactors, s, owner);
+        if (rc0 != PSB_OK) return rc0;
+    }
 #endif
 #ifndef PSB_EMU
     // inverse row transform of a chunk + epilogue: t = exp(i*sigma*V) (and optionally V), or the bare phases
@@ -209,7 +213,7 @@ static int build_eager(const int32_t* offsets, const uint32_t* ux, const uint32_
             int rc;
 #ifndef PSB_EMU
             if (sf_nufft)
-                rc = launch_sf_nufft(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, formfactors, f2(scratch), s, owner);
+                rc = launch_sf_nufft(offsets, ux, uy, 2 * n_atoms, nz, ntypes, nx, ny, n_frames, f0, nf, mb, nm, formfactors, f2(scratch), s, owner);
             else if (sf_fast)
                 rc = launch_sf_fast(sp.offsets, sp.ux, sp.uy, sp.cap, nz, ntypes, nx, ny, mb, nm, nf, f2(scratch), s, owner);
             else

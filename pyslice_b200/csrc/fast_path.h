@@ -49,9 +49,12 @@ void sf_mode_set(int mode);      // 0 auto (default), 1 direct sum always, 2 NUF
 int sf_mode();
 bool sf_nufft_supported(int ntypes, int nx, int ny);
 bool sf_nufft_wanted(int ntypes, int nx, int ny, int n_atoms, int nz);
+// sf_nufft_prepare: once per build call over all n_frames (offsets / ux / uy of frame 0); launch_sf_nufft: per chunk
+int sf_nufft_prepare(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
+                     int ny, int n_frames, const float* ff, cudaStream_t s, cudaStream_t owner);
 int launch_sf_nufft(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
-                    int ny, int pair_begin, int pair_count, int nf, const float* ff, float2* out, cudaStream_t s,
-                    cudaStream_t owner);
+                    int ny, int n_frames, int frame0, int nf, int pair_begin, int pair_count, const float* ff, float2* out,
+                    cudaStream_t s, cudaStream_t owner);
 void sf_nufft_release();      // the pipelined kernel stages at most 64 atom types; beyond that the generic kernel runs
 
 }  // namespace psb

@@ -15,7 +15,7 @@
 //
 //   K1  nufft_prep_kernel   one CTA per (slice pair, frame): orders the pair's atoms by (type, x bin of 16 fine cells) --
 //                           deterministically: ties keep list order -- and sums the (Nyquist, Nyquist) corner term.
-//   K2  nufft_cols_kernel   one CTA per (W adjacent ky columns, slice pair, frame): builds the G tile in shared memory
+//   K2  nufft_cols_kernel   persistent, one CTA per SM walking (W adjacent ky columns, slice pair, frame) tiles: builds the G tile in shared memory
 //                           (thread (column, bin) spreads the atoms of its bin; even bins, then odd bins, so no two threads
 //                           touch a cell at the same time and the sums are reproducible), transforms it in place
 //                           (fast_fft.cuh: radix 16 x 8 x 16 for M = 2048, 16 x 4 x 16 for M = 1024), keeps the nx low
@@ -54,18 +54,19 @@ constexpr int kMaxKeys = 8192;          // ntypes * bins the ordering kernel can
 std::atomic<int> g_sf_mode{0};          // 0 auto, 1 direct sum always, 2 NUFFT wherever it is supported
 
 struct NufftParams {
-    const int* offsets;         // (nf, nseg+1), first frame of the chunk
-    const unsigned int* ux;     // (nf, cap) fixed-point fractions, grouped by (slice, type) segment
+    const int* offsets;         // (F, nseg+1), first frame of the CALL (K1 covers every frame and pair of it at once)
+    const unsigned int* ux;     // (F, cap) fixed-point fractions, grouped by (slice, type) segment
     const unsigned int* uy;
     int cap, nz, ntypes, nx, ny;
-    int pair_begin, pair_count;
+    int npairs;                 // slice pairs per frame
+    int frame0, pair_begin, pair_count;     // K2: this chunk covers frames [frame0, frame0 + nf) x pairs [pair_begin, pair_begin + pair_count)
     int nb, log_m;              // x bins per pair (= M / 16), log2(M)
     // written by K1, read by K2
-    int* xoff;                  // (nf, pair_count, ntypes*nb + 1) offsets into the pair's record range, by (type, bin)
-    unsigned int* rx;           // (nf, cap) records of a pair, ordered by (type, bin), list order inside
+    int* xoff;                  // (F, npairs, ntypes*nb + 1) offsets into the pair's record range, by (type, bin)
+    unsigned int* rx;           // (F, cap) records of a pair, ordered by (type, bin), list order inside
     unsigned int* ry;
     unsigned int* rpar;         // 0: first slice of the pair (real part), 1: second (imaginary part)
-    float* corner;              // (nf, pair_count, ntypes, 2)  sum sin(pi nx u) sin(pi ny v) per type and slice of the pair
+    float* corner;              // (F, npairs, ntypes, 2)  sum sin(pi nx u) sin(pi ny v) per type and slice of the pair
     const float* ff;            // (ntypes, nx, ny) form factors
     const float* dec;           // (nx) 1 / phi_hat(kx / M)
     const float2* tw;           // staged twiddles of the M-point plan
@@ -82,8 +83,7 @@ __global__ void __launch_bounds__(256) nufft_prep_kernel(const NufftParams p) {
     double* red = reinterpret_cast<double*>(smem_raw);                 // reduction scratch (reused after the ordering)
     constexpr int kChunk = 4096;
     const int t = threadIdx.x;
-    const int ml = blockIdx.x, f = blockIdx.y;
-    const int m = p.pair_begin + ml;
+    const int m = blockIdx.x, f = blockIdx.y;                          // every pair of every frame of the call
     const int nseg = p.nz * p.ntypes;
     const int* off = p.offsets + (long long)f * (nseg + 1);
     const int s0 = 2 * m, s1 = (2 * m + 2 < p.nz) ? 2 * m + 2 : p.nz;
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) nufft_prep_kernel(const NufftParams p) {
         }
         __syncthreads();
     }
-    int* xoff = p.xoff + ((long long)f * p.pair_count + ml) * (nkeys + 1);
+    int* xoff = p.xoff + ((long long)f * p.npairs + m) * (nkeys + 1);
     for (int k = t; k <= nkeys; k += 256) xoff[k] = hist[k];
     // position of atom i = hist[key] + number of earlier list entries with the same key (stable, hence reproducible)
     unsigned int* rx = p.rx + (long long)f * p.cap + begin;
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(256) nufft_prep_kernel(const NufftParams p) {
             if (t < h) red[t] += red[t + h];
             __syncthreads();
         }
-        if (t == 0) p.corner[(((long long)f * p.pair_count + ml) * p.ntypes + typ) * 2 + par] = (float)red[0];
+        if (t == 0) p.corner[(((long long)f * p.npairs + m) * p.ntypes + typ) * 2 + par] = (float)red[0];
         __syncthreads();
     }
 }
@@ -185,7 +185,7 @@ struct NufftCfg {
     static constexpr int kRows = M + M / 16;         // padded
     static constexpr size_t kTileBytes = (size_t)kRows * W * sizeof(float2);
     static constexpr int kStage = 1536;              // records of one atom type staged in shared memory (more: read from L2)
-    static constexpr size_t kSmem = kTileBytes + 3 * kStage * sizeof(unsigned int) + (T + 1) * sizeof(int);
+    static constexpr size_t kSmem = kTileBytes + 3 * kStage * sizeof(unsigned int) + (T + 1) * sizeof(int) + (M / 2) * sizeof(float);
     static constexpr int kLogM = M == 2048 ? 11 : 10;
 };
 
@@ -227,32 +227,26 @@ __device__ __forceinline__ float2 unit_phase_fast(int m, unsigned int v) {
 }
 
 template <int M>
-__global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(const NufftParams p) {
+__global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(const NufftParams p, const int n_tiles) {
     using C = NufftCfg<M>;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* tile = reinterpret_cast<float2*>(smem_raw);
-    unsigned int* s_rx = reinterpret_cast<unsigned int*>(smem_raw + C::kTileBytes);      // [kStage] records of the current type
+    unsigned int* s_rx = reinterpret_cast<unsigned int*>(smem_raw + C::kTileBytes);      // [kStage] records of the current (pair, type)
     unsigned int* s_ry = s_rx + C::kStage;
     unsigned int* s_rp = s_ry + C::kStage;
     int* s_xoff = reinterpret_cast<int*>(s_rp + C::kStage);                              // [T + 1]
+    float* s_dec = reinterpret_cast<float*>(s_xoff + C::T + 1);                          // [nx]
     const int tid = threadIdx.x, c = tid % C::W, j = tid / C::W;
-    const int my = blockIdx.x * C::W + c;                        // column, fft order
-    const int ml = blockIdx.y, f = blockIdx.z;
-    const int nx = M / 2;
+    constexpr int nx = M / 2;
+    // persistent CTA: twiddles and the deconvolution table are loaded once, a contiguous range of (frame, pair, column
+    // tile) triples is walked pair by pair so a pair's records are staged once for all of its column tiles
     fast::Twiddles<M> tw;
     tw.load(p.tw, j);
+    for (int i = tid; i < nx; i += C::kThreads) s_dec[i] = p.dec[i];
     const NufftXchg<M> xc{reinterpret_cast<cpx*>(tile), c};
-    const int msy = my < (p.ny + 1) / 2 ? my : my - p.ny;
-    const bool nyq_y = (p.ny % 2 == 0) && my == p.ny / 2;
     const int nkeys = p.ntypes * C::T;
-    const int* xoff = p.xoff + ((long long)f * p.pair_count + ml) * (nkeys + 1);
-    const int m = p.pair_begin + ml;
     const int nseg = p.nz * p.ntypes;
-    const long long rbase = (long long)f * p.cap + p.offsets[(long long)f * (nseg + 1) + 2 * m * p.ntypes];
-    const unsigned int* rx = p.rx + rbase;
-    const unsigned int* ry = p.ry + rbase;
-    const unsigned int* rpar = p.rpar + rbase;
-    const float* corner = p.corner + ((long long)f * p.pair_count + ml) * p.ntypes * 2;
+    const int tiles_per_pair = p.ny / C::W;
     constexpr unsigned int kFracBits = 32 - C::kLogM;
     constexpr float kFracScale = 1.0f / (float)(1u << kFracBits);
     // Spreading runs in its own thread -> (column, bin) map: a warp holds bins of ONE parity (its W lanes per bin are the
@@ -264,94 +258,118 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     constexpr int kWeightsPerLane = kTaps / C::W;                 // 2 (W = 4) or 1 (W = 8)
     const int sbin = 2 * (kBinsPerWarp * (warp >> 1) + lane / C::W) + (warp & 1);
     const int group0 = lane & ~(C::W - 1);
+    const int tile0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
+    const int tile1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
+    int staged_img = -1;
 
-    cpx acc_out[8];
+    for (int tix = tile0; tix < tile1; ++tix) {
+        const int img = tix / tiles_per_pair;                    // frame * pair_count + pair-in-chunk
+        const int my = (tix - img * tiles_per_pair) * C::W + c;  // column, fft order
+        const int fl = img / p.pair_count, ml = img - fl * p.pair_count;
+        const int f = p.frame0 + fl, m = p.pair_begin + ml;
+        const int msy = my < (p.ny + 1) / 2 ? my : my - p.ny;
+        const bool nyq_y = (p.ny % 2 == 0) && my == p.ny / 2;
+        const int* xoff = p.xoff + ((long long)f * p.npairs + m) * (nkeys + 1);
+        const long long rbase = (long long)f * p.cap + p.offsets[(long long)f * (nseg + 1) + 2 * m * p.ntypes];
+        const unsigned int* rx = p.rx + rbase;
+        const unsigned int* ry = p.ry + rbase;
+        const unsigned int* rpar = p.rpar + rbase;
+        const float* corner = p.corner + ((long long)f * p.npairs + m) * p.ntypes * 2;
+        cpx acc_out[8];
 #pragma unroll
-    for (int s = 0; s < 8; ++s) acc_out[s] = fast::c_make(0.f, 0.f);
+        for (int s = 0; s < 8; ++s) acc_out[s] = fast::c_make(0.f, 0.f);
 
-    for (int z = 0; z < p.ntypes; ++z) {
-        // ---- stage this type's records and bin offsets, clear the tile
-        const int r0 = xoff[z * C::T], r1 = xoff[(z + 1) * C::T];
-        const int nstage = (r1 - r0) < C::kStage ? (r1 - r0) : C::kStage;
-        for (int i = tid; i < nstage; i += C::kThreads) {
-            s_rx[i] = rx[r0 + i];
-            s_ry[i] = ry[r0 + i];
-            s_rp[i] = rpar[r0 + i];
-        }
-        for (int i = tid; i <= C::T; i += C::kThreads) s_xoff[i] = xoff[z * C::T + i] - r0;
+        for (int z = 0; z < p.ntypes; ++z) {
+            // form factors of this tile's 8 rows per thread: issued now, needed after the transform
+            float g8[8];
+            {
+                const float* ffz = p.ff + ((long long)z * nx) * p.ny + my;
 #pragma unroll
-        for (int rr = 0; rr < 16; ++rr) tile[xc.at(16 * j + rr)] = make_float2(0.f, 0.f);
-        __syncthreads();
-        // ---- spread: rows = fine cells, this lane's column
-        for (int phase = 0; phase < 2; ++phase) {
-            if ((warp & 1) == phase) {
-                const int i0 = s_xoff[sbin], i1 = s_xoff[sbin + 1];
-                int trips = i1 - i0;
+                for (int s = 0; s < 8; ++s) g8[s] = __ldg(ffz + (long long)(j + C::T * s) * p.ny);
+            }
+            // ---- stage this (pair, type)'s records and bin offsets (kept across the pair's column tiles when there is
+            //      one atom type), clear the tile
+            const int r0 = xoff[z * C::T], r1 = xoff[(z + 1) * C::T];
+            if (p.ntypes > 1 || staged_img != img) {
+                const int nstage = (r1 - r0) < C::kStage ? (r1 - r0) : C::kStage;
+                for (int i = tid; i < nstage; i += C::kThreads) {
+                    s_rx[i] = rx[r0 + i];
+                    s_ry[i] = ry[r0 + i];
+                    s_rp[i] = rpar[r0 + i];
+                }
+                for (int i = tid; i <= C::T; i += C::kThreads) s_xoff[i] = xoff[z * C::T + i] - r0;
+                staged_img = img;
+            }
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));
-                for (int it = 0; it < trips; ++it) {
-                    const int i = i0 + it;
-                    const bool live = i < i1;
-                    unsigned int u = 0, v = 0, par = 0;
-                    if (live) {
-                        if (i < C::kStage) { u = s_rx[i]; v = s_ry[i]; par = s_rp[i]; }
-                        else { u = rx[r0 + i]; v = ry[r0 + i]; par = rpar[r0 + i]; }
-                    }
-                    float2 e = nyq_y ? make_float2(unit_phase_fast(p.ny / 2, v).x, 0.f)      // cos(pi ny v): the Hermitian part
-                                     : unit_phase_fast(msy, v);
-                    if (par) e = make_float2(-e.y, e.x);                                      // second slice of the pair: times i
-                    const int cell = (int)(u >> kFracBits);
-                    const float fr = (float)(u & ((1u << kFracBits) - 1u)) * kFracScale;
-                    float wl[kWeightsPerLane];
+            for (int rr = 0; rr < 16; ++rr) tile[xc.at(16 * j + rr)] = make_float2(0.f, 0.f);
+            __syncthreads();
+            // ---- spread: rows = fine cells, this lane's column
+            for (int phase = 0; phase < 2; ++phase) {
+                if ((warp & 1) == phase) {
+                    const int i0 = s_xoff[sbin], i1 = s_xoff[sbin + 1];
+                    int trips = i1 - i0;
 #pragma unroll
-                    for (int q = 0; q < kWeightsPerLane; ++q) wl[q] = es_weight((float)(c * kWeightsPerLane + q - 3) - fr);
-#pragma unroll
-                    for (int k = 0; k < kTaps; ++k) {
-                        const float w = __shfl_sync(0xffffffffu, wl[k % kWeightsPerLane], group0 + k / kWeightsPerLane);
+                    for (int o = 16; o > 0; o >>= 1) trips = max(trips, __shfl_xor_sync(0xffffffffu, trips, o));
+                    for (int it = 0; it < trips; ++it) {
+                        const int i = i0 + it;
+                        const bool live = i < i1;
+                        unsigned int u = 0, v = 0, par = 0;
                         if (live) {
-                            const int idx = xc.at((cell - 3 + k) & (M - 1));
-                            float2 g = tile[idx];
-                            g.x = fmaf(w, e.x, g.x);
-                            g.y = fmaf(w, e.y, g.y);
-                            tile[idx] = g;
+                            if (i < C::kStage) { u = s_rx[i]; v = s_ry[i]; par = s_rp[i]; }
+                            else { u = rx[r0 + i]; v = ry[r0 + i]; par = rpar[r0 + i]; }
+                        }
+                        float2 e = nyq_y ? make_float2(unit_phase_fast(p.ny / 2, v).x, 0.f)      // cos(pi ny v): the Hermitian part
+                                         : unit_phase_fast(msy, v);
+                        if (par) e = make_float2(-e.y, e.x);                                      // second slice of the pair: times i
+                        const int cell = (int)(u >> kFracBits);
+                        const float fr = (float)(u & ((1u << kFracBits) - 1u)) * kFracScale;
+                        float wl[kWeightsPerLane];
+#pragma unroll
+                        for (int q = 0; q < kWeightsPerLane; ++q) wl[q] = es_weight((float)(c * kWeightsPerLane + q - 3) - fr);
+#pragma unroll
+                        for (int k = 0; k < kTaps; ++k) {
+                            const float w = __shfl_sync(0xffffffffu, wl[k % kWeightsPerLane], group0 + k / kWeightsPerLane);
+                            if (live) {
+                                const int idx = xc.at((cell - 3 + k) & (M - 1));
+                                float2 g = tile[idx];
+                                g.x = fmaf(w, e.x, g.x);
+                                g.y = fmaf(w, e.y, g.y);
+                                tile[idx] = g;
+                            }
                         }
                     }
                 }
+                __syncthreads();
             }
+            // ---- M-point transform along x, in place in the tile
+            cpx v16[16];
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v16[e] = reinterpret_cast<const cpx*>(tile)[xc.at(j + e * C::T)];
             __syncthreads();
+            cpx nyq_hold = fast::c_make(0.f, 0.f);
+            fast::line_fft<M, -1>(
+                [&](int e) { return v16[e]; },
+                [&](int t, cpx a) {
+                    // fine frequency j + T*t; kept: t in {0..3} (kx >= 0) and {12..15} (kx < 0), coarse row kxi = j + T*s
+                    if (t >= 4 && t < 12) {
+                        if (t == 4) nyq_hold = a;                    // +nx/2 (j == 0 only)
+                        return;
+                    }
+                    const int s = t < 4 ? t : t - 8;
+                    const float dk = s_dec[j + C::T * s];
+                    if (s == 4 && j == 0) {                          // kx Nyquist row: mean of the +nx/2 and -nx/2 outputs
+                        a = fast::mul2(fast::add2(a, nyq_hold), fast::c_make(0.5f, 0.5f));
+                        if (nyq_y)                                    // corner: cos cos - sin sin
+                            a = fast::sub2(a, fast::c_make(corner[2 * z] / dk, corner[2 * z + 1] / dk));
+                    }
+                    const float g = g8[s < 8 ? s : 0] * dk;
+                    acc_out[s < 8 ? s : 0] = fast::fma2(a, fast::c_make(g, g), acc_out[s < 8 ? s : 0]);
+                },
+                tw, j, xc, 0);
         }
-        // ---- M-point transform along x, in place in the tile
-        cpx v16[16];
+        float2* out = p.out + ((long long)img * nx) * p.ny + my;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v16[e] = reinterpret_cast<const cpx*>(tile)[xc.at(j + e * C::T)];
-        __syncthreads();
-        const float* ffz = p.ff + ((long long)z * nx) * p.ny + my;
-        cpx nyq_hold = fast::c_make(0.f, 0.f);
-        fast::line_fft<M, -1>(
-            [&](int e) { return v16[e]; },
-            [&](int t, cpx a) {
-                // fine frequency j + T*t; kept: t in {0..3} (kx >= 0) and {12..15} (kx < 0), coarse row kxi = j + T*s
-                if (t >= 4 && t < 12) {
-                    if (t == 4) nyq_hold = a;                    // +nx/2 (j == 0 only)
-                    return;
-                }
-                const int s = t < 4 ? t : t - 8;
-                const int kxi = j + C::T * s;
-                if (s == 4 && j == 0) {                          // kx Nyquist row: mean of the +nx/2 and -nx/2 outputs
-                    a = fast::mul2(fast::add2(a, nyq_hold), fast::c_make(0.5f, 0.5f));
-                    if (nyq_y)                                    // corner: cos cos - sin sin
-                        a = fast::sub2(a, fast::c_make(corner[2 * z] / p.dec[kxi], corner[2 * z + 1] / p.dec[kxi]));
-                }
-                const float g = ffz[(long long)kxi * p.ny] * p.dec[kxi];
-                acc_out[s < 8 ? s : 0] = fast::fma2(a, fast::c_make(g, g), acc_out[s < 8 ? s : 0]);
-            },
-            tw, j, xc, 0);
-    }
-    float2* out = p.out + (((long long)f * p.pair_count + ml) * nx) * p.ny + my;
-#pragma unroll
-    for (int s = 0; s < 8; ++s) {
-        const int kxi = j + C::T * s;
-        out[(long long)kxi * p.ny] = make_float2(fast::c_re(acc_out[s]), fast::c_im(acc_out[s]));
+        for (int s = 0; s < 8; ++s) out[(long long)(j + C::T * s) * p.ny] = make_float2(fast::c_re(acc_out[s]), fast::c_im(acc_out[s]));
     }
 }
 
@@ -410,7 +428,10 @@ int cols_go(const NufftParams& p, int nf, cudaStream_t s) {
         return (int)PSB_OK;
     });
     if (rc0 != PSB_OK) return rc0;
-    nufft_cols_kernel<M><<<dim3(p.ny / C::W, p.pair_count, nf), C::kThreads, C::kSmem, s>>>(p);
+    const long long n_tiles = (long long)(p.ny / C::W) * p.pair_count * nf;
+    if (n_tiles > 0x7fffffffLL) return fail(PSB_ERR_UNSUPPORTED, "nufft columns: too many tiles per launch");
+    const int sms = rt::sm_count();
+    nufft_cols_kernel<M><<<dim3((unsigned)(n_tiles < sms ? n_tiles : sms)), C::kThreads, C::kSmem, s>>>(p, (int)n_tiles);
     ++launch_counter();
     return rt::check("nufft columns launch");
 }
@@ -452,16 +473,17 @@ void sf_nufft_release() {
     g_dec.clear();
 }
 
-int launch_sf_nufft(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
-                    int ny, int pair_begin, int pair_count, int nf, const float* ff, float2* out, cudaStream_t s,
-                    cudaStream_t owner) {
+namespace {
+// workspace + tables of a call, resolved once per (device, owner stream); K1 fills it for the whole call
+int nufft_params(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx, int ny,
+                 int n_frames, const float* ff, cudaStream_t owner, bool may_grow, NufftParams* out) {
     if (!sf_nufft_supported(ntypes, nx, ny)) return fail(PSB_ERR_UNSUPPORTED, "nufft structure factor: unsupported grid");
     const int M = 2 * nx;
     NufftParams p;
     std::memset(&p, 0, sizeof(p));
     p.offsets = offsets; p.ux = ux; p.uy = uy; p.cap = cap; p.nz = nz; p.ntypes = ntypes; p.nx = nx; p.ny = ny;
-    p.pair_begin = pair_begin; p.pair_count = pair_count; p.nb = M / 16; p.log_m = M == 2048 ? 11 : 10;
-    p.ff = ff; p.out = out;
+    p.npairs = (nz + 1) / 2; p.nb = M / 16; p.log_m = M == 2048 ? 11 : 10;
+    p.ff = ff;
     int rc = dec_table(nx, &p.dec, owner);
     if (rc != PSB_OK) return rc;
     FftTables tb;
@@ -472,28 +494,40 @@ int launch_sf_nufft(const int* offsets, const unsigned int* ux, const unsigned i
     if (blue || N != M) return fail(PSB_ERR_UNSUPPORTED, "nufft structure factor: power-of-two fine grid expected");
     p.tw = tb.tw;
     const int nkeys = ntypes * p.nb;
-    const size_t n_xoff = (size_t)nf * pair_count * (nkeys + 1), n_rec = (size_t)nf * cap, n_corner = (size_t)nf * pair_count * ntypes * 2;
+    const size_t n_xoff = (size_t)n_frames * p.npairs * (nkeys + 1), n_rec = (size_t)n_frames * cap;
+    const size_t n_corner = (size_t)n_frames * p.npairs * ntypes * 2;
     const size_t need = n_xoff * sizeof(int) + 3 * n_rec * sizeof(unsigned int) + n_corner * sizeof(float) + 256;
-    {
-        std::lock_guard<std::mutex> lk(g_mu);
-        NufftWorkspace& w = g_ws[std::make_pair(rt::device(), owner)];
-        if (need > w.bytes) {
-            cudaError_t e = cudaStreamSynchronize(owner);      // kernels of earlier chunks may still read the old block
-            if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("nufft workspace sync: ") + cudaGetErrorString(e));
-            graph_cache_release();                             // recorded launch sequences point at the block freed here
-            rt::dev_free(w.block);
-            w.block = rt::dev_alloc(need);
-            w.bytes = w.block ? need : 0;
-            if (!w.block) return PSB_ERR_NOMEM;
-        }
-        p.xoff = reinterpret_cast<int*>(w.block);
-        p.rx = reinterpret_cast<unsigned int*>(p.xoff + n_xoff);
-        p.ry = p.rx + n_rec;
-        p.rpar = p.ry + n_rec;
-        p.corner = reinterpret_cast<float*>(p.rpar + n_rec);
+    std::lock_guard<std::mutex> lk(g_mu);
+    NufftWorkspace& w = g_ws[std::make_pair(rt::device(), owner)];
+    if (need > w.bytes) {
+        if (!may_grow) return fail(PSB_ERR_INVALID, "launch_sf_nufft without sf_nufft_prepare");
+        cudaError_t e = cudaStreamSynchronize(owner);          // kernels of earlier calls may still read the old block
+        if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("nufft workspace sync: ") + cudaGetErrorString(e));
+        graph_cache_release();                                 // recorded launch sequences point at the block freed here
+        rt::dev_free(w.block);
+        w.block = rt::dev_alloc(need);
+        w.bytes = w.block ? need : 0;
+        if (!w.block) return PSB_ERR_NOMEM;
     }
-    const size_t prep_smem = (size_t)(nkeys + 1 + 256) * sizeof(int) + 4096 * sizeof(unsigned short) + 16;
-    const size_t prep_smem2 = prep_smem < 256 * sizeof(double) ? 256 * sizeof(double) : prep_smem;
+    p.xoff = reinterpret_cast<int*>(w.block);
+    p.rx = reinterpret_cast<unsigned int*>(p.xoff + n_xoff);
+    p.ry = p.rx + n_rec;
+    p.rpar = p.ry + n_rec;
+    p.corner = reinterpret_cast<float*>(p.rpar + n_rec);
+    *out = p;
+    return PSB_OK;
+}
+}  // namespace
+
+// once per psb_build_* call: order the atoms of every (frame, slice pair) by (type, x bin) and take the corner sums
+int sf_nufft_prepare(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
+                     int ny, int n_frames, const float* ff, cudaStream_t s, cudaStream_t owner) {
+    NufftParams p;
+    int rc = nufft_params(offsets, ux, uy, cap, nz, ntypes, nx, ny, n_frames, ff, owner, true, &p);
+    if (rc != PSB_OK) return rc;
+    const int nkeys = ntypes * p.nb;
+    size_t prep_smem = (size_t)(nkeys + 1 + 256) * sizeof(int) + 4096 * sizeof(unsigned short) + 16;
+    if (prep_smem < 256 * sizeof(double)) prep_smem = 256 * sizeof(double);
     static rt::PerDeviceOnce once;
     rc = once.run([] {
         cudaError_t e = cudaFuncSetAttribute(nufft_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
@@ -501,11 +535,20 @@ int launch_sf_nufft(const int* offsets, const unsigned int* ux, const unsigned i
         return (int)PSB_OK;
     });
     if (rc != PSB_OK) return rc;
-    nufft_prep_kernel<<<dim3(pair_count, nf), 256, prep_smem2, s>>>(p);
+    nufft_prep_kernel<<<dim3(p.npairs, n_frames), 256, prep_smem, s>>>(p);
     ++launch_counter();
-    rc = rt::check("nufft prep launch");
+    return rt::check("nufft prep launch");
+}
+
+// per chunk: frames [frame0, frame0 + nf) x pairs [pair_begin, pair_begin + pair_count) -> out (nf, pair_count, nx, ny)
+int launch_sf_nufft(const int* offsets, const unsigned int* ux, const unsigned int* uy, int cap, int nz, int ntypes, int nx,
+                    int ny, int n_frames, int frame0, int nf, int pair_begin, int pair_count, const float* ff, float2* out,
+                    cudaStream_t s, cudaStream_t owner) {
+    NufftParams p;
+    int rc = nufft_params(offsets, ux, uy, cap, nz, ntypes, nx, ny, n_frames, ff, owner, false, &p);
     if (rc != PSB_OK) return rc;
-    return M == 2048 ? cols_go<2048>(p, nf, s) : cols_go<1024>(p, nf, s);
+    p.frame0 = frame0; p.pair_begin = pair_begin; p.pair_count = pair_count; p.out = out;
+    return 2 * nx == 2048 ? cols_go<2048>(p, nf, s) : cols_go<1024>(p, nf, s);
 }
 
 }  // namespace psb
