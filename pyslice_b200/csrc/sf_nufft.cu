@@ -66,12 +66,39 @@ struct NufftParams {
     unsigned int* rx;           // (F, cap) records of a pair, ordered by (type, bin), list order inside
     unsigned int* ry;
     unsigned int* rpar;         // 0: first slice of the pair (real part), 1: second (imaginary part)
+    float* rwt;                 // (F, cap, 8) the record's eight tap weights phi(k - 3 - frac), k = 0..7 (tap rows: cell - 3 + k)
     float* corner;              // (F, npairs, ntypes, 2)  sum sin(pi nx u) sin(pi ny v) per type and slice of the pair
     const float* ff;            // (ntypes, nx, ny) form factors
     const float* dec;           // (nx) 1 / phi_hat(kx / M)
     const float2* tw;           // staged twiddles of the M-point plan
     float2* out;                // (nf, pair_count, nx, ny)
 };
+
+// phi(z) = exp(beta (sqrt(1 - z^2/16) - 1)), |z| <= 4, through the SFU with one correction step each (relative error
+// ~2e-7; the library sqrtf / expf cost 5 x the instructions, and a tile evaluates ~40 000 weights)
+__device__ __forceinline__ float es_weight(float z) {
+    const float s = fmaxf(fmaf(-z * z, 1.0f / 16.0f, 1.0f), 1e-30f);
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
+    float q = s * r;                                             // ~sqrt(s)
+    q = fmaf(0.5f * r, fmaf(-q, q, s), q);                       // one Newton step
+    const float x = kBeta * (q - 1.0f);                          // in [-beta, 0]
+    const float kL2e = 1.4426950408889634f, kL2eLo = 1.925963033500e-8f;
+    const float t = x * kL2e;
+    const float rem = fmaf(x, kL2e, -t) + x * kL2eLo;            // what the rounding of t lost, in units of log2
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return fmaf(e, rem * 0.6931471805599453f, e);
+}
+
+// exp(-2*pi*i*m*v) with v a 32-bit turn fraction: exact integer phase reduction, then the SFU on an angle in [-pi, pi)
+// (absolute error ~4e-7, the accuracy of the direct kernels' phase tables, sf_fast.cu)
+__device__ __forceinline__ float2 unit_phase_fast(int m, unsigned int v) {
+    const int ph = (int)((unsigned int)m * v);
+    float sn, cs;
+    __sincosf((float)ph * (3.14159265358979323846f * 4.656612873077393e-10f), &sn, &cs);
+    return make_float2(cs, -sn);
+}
 
 // ---- K1 ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) nufft_prep_kernel(const NufftParams p) {
@@ -149,9 +176,15 @@ __global__ void __launch_bounds__(256) nufft_prep_kernel(const NufftParams p) {
         }
         if (i < n) {
             const int pos = hist[key] + same;
-            rx[pos] = ux[begin + i];
+            const unsigned int u = ux[begin + i];
+            rx[pos] = u;
             ry[pos] = uy[begin + i];
             rpar[pos] = (unsigned int)par;
+            const unsigned int frac_bits = 32 - p.log_m;
+            const float fr = (float)(u & ((1u << frac_bits) - 1u)) * (1.0f / (float)(1u << frac_bits));
+            float4* wq = reinterpret_cast<float4*>(p.rwt + ((long long)f * p.cap + begin + pos) * kTaps);
+            wq[0] = make_float4(es_weight(-3.f - fr), es_weight(-2.f - fr), es_weight(-1.f - fr), es_weight(0.f - fr));
+            wq[1] = make_float4(es_weight(1.f - fr), es_weight(2.f - fr), es_weight(3.f - fr), es_weight(4.f - fr));
         }
     }
     // corner term per (type, slice of the pair): sum sin(pi nx u) sin(pi ny v), fixed summation order
@@ -184,9 +217,9 @@ struct NufftCfg {
     static constexpr int W = kThreads / T;           // columns per tile: 4 (M = 2048), 8 (M = 1024)
     static constexpr int kRows = M + M / 16;         // padded
     static constexpr size_t kTileBytes = (size_t)kRows * W * sizeof(float2);
-    static constexpr int kStage = 1536;              // records of one atom type staged in shared memory (more: read from L2)
+    static constexpr int kStage = W == 4 ? 1536 : 1024;      // records of one atom type staged in shared memory (more: read from L2)
     static constexpr size_t kEOffset = (kTileBytes + 3 * kStage * sizeof(unsigned int) + (T + 1) * sizeof(int) + (M / 2) * sizeof(float) + 15) / 16 * 16;
-    static constexpr size_t kSmem = kEOffset + (size_t)kStage * W * sizeof(float2);
+    static constexpr size_t kSmem = kEOffset + (size_t)kStage * W * sizeof(float2) + (size_t)kStage * 8 * sizeof(float);
     static constexpr int kLogM = M == 2048 ? 11 : 10;
 };
 
@@ -201,32 +234,6 @@ struct NufftXchg {
     __device__ __forceinline__ void mid_sync(int) const { __syncthreads(); }
 };
 
-// phi(z) = exp(beta (sqrt(1 - z^2/16) - 1)), |z| <= 4, through the SFU with one correction step each (relative error
-// ~2e-7; the library sqrtf / expf cost 5 x the instructions, and a tile evaluates ~40 000 weights)
-__device__ __forceinline__ float es_weight(float z) {
-    const float s = fmaxf(fmaf(-z * z, 1.0f / 16.0f, 1.0f), 1e-30f);
-    float r;
-    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(s));
-    float q = s * r;                                             // ~sqrt(s)
-    q = fmaf(0.5f * r, fmaf(-q, q, s), q);                       // one Newton step
-    const float x = kBeta * (q - 1.0f);                          // in [-beta, 0]
-    const float kL2e = 1.4426950408889634f, kL2eLo = 1.925963033500e-8f;
-    const float t = x * kL2e;
-    const float rem = fmaf(x, kL2e, -t) + x * kL2eLo;            // what the rounding of t lost, in units of log2
-    float e;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
-    return fmaf(e, rem * 0.6931471805599453f, e);
-}
-
-// exp(-2*pi*i*m*v) with v a 32-bit turn fraction: exact integer phase reduction, then the SFU on an angle in [-pi, pi)
-// (absolute error ~4e-7, the accuracy of the direct kernels' phase tables, sf_fast.cu)
-__device__ __forceinline__ float2 unit_phase_fast(int m, unsigned int v) {
-    const int ph = (int)((unsigned int)m * v);
-    float sn, cs;
-    __sincosf((float)ph * (3.14159265358979323846f * 4.656612873077393e-10f), &sn, &cs);
-    return make_float2(cs, -sn);
-}
-
 template <int M>
 __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(const NufftParams p, const int n_tiles) {
     using C = NufftCfg<M>;
@@ -238,6 +245,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     int* s_xoff = reinterpret_cast<int*>(s_rp + C::kStage);                              // [T + 1]
     float* s_dec = reinterpret_cast<float*>(s_xoff + C::T + 1);                          // [nx]
     float2* s_e = reinterpret_cast<float2*>(smem_raw + C::kEOffset);                     // [kStage][W] exp(-2 pi i ky y) per record and column
+    float* s_w = reinterpret_cast<float*>(s_e + (size_t)C::kStage * C::W);               // [kStage][8] tap weights
     const int tid = threadIdx.x, c = tid % C::W, j = tid / C::W;
     constexpr int nx = M / 2;
     // persistent CTA: twiddles and the deconvolution table are loaded once, a contiguous range of (frame, pair, column
@@ -280,6 +288,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
         const unsigned int* rx = p.rx + rbase;
         const unsigned int* ry = p.ry + rbase;
         const unsigned int* rpar = p.rpar + rbase;
+        const float* rwt = p.rwt + rbase * kTaps;
         const float* corner = p.corner + ((long long)f * p.npairs + m) * p.ntypes * 2;
         cpx acc_out[8];
 #pragma unroll
@@ -303,6 +312,8 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                     s_ry[i] = ry[r0 + i];
                     s_rp[i] = rpar[r0 + i];
                 }
+                for (int i = tid; i < nstage * 2; i += C::kThreads)
+                    reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(rwt + (long long)r0 * kTaps)[i];
                 for (int i = tid; i <= C::T; i += C::kThreads) s_xoff[i] = xoff[z * C::T + i] - r0;
                 staged_img = img;
             }
@@ -327,24 +338,23 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                 const int bin = (bb + C::T) % C::T;
                 const int i0 = s_xoff[bin], i1 = s_xoff[bin + 1];
                 for (int i = i0; i < i1; ++i) {
-                    unsigned int u;
+                    // lane (tap k, column c): row, weight and phase factor of this record (staged, or from L2 beyond kStage)
+                    const bool staged = i < C::kStage;
+                    const unsigned int u = staged ? s_rx[i] : rx[r0 + i];
                     float2 e;
-                    if (i < C::kStage) {
-                        u = s_rx[i];
+                    if (staged) {
                         e = s_e[i * C::W + c];
-                    } else {                                     // more records than the staging area holds: from L2
-                        u = rx[r0 + i];
+                    } else {
                         e = nyq_y ? make_float2(unit_phase_fast(p.ny / 2, ry[r0 + i]).x, 0.f) : unit_phase_fast(msy, ry[r0 + i]);
                         if (rpar[r0 + i]) e = make_float2(-e.y, e.x);
                     }
                     const int cell = (int)(u >> kFracBits);
-                    const float fr = (float)(u & ((1u << kFracBits) - 1u)) * kFracScale;
 #pragma unroll
                     for (int q = 0; q < kTapsPerLane; ++q) {
                         const int k = tap0 + kTapStride * q;
                         const int row = (cell - 3 + k) & (M - 1);
                         if ((row >> kLogRW) == warp) {
-                            const float w = es_weight((float)(k - 3) - fr);
+                            const float w = staged ? s_w[i * kTaps + k] : rwt[(long long)(r0 + i) * kTaps + k];
                             const int idx = xc.at(row);
                             float2 g = tile[idx];
                             g.x = fmaf(w, e.x, g.x);
@@ -511,7 +521,7 @@ int nufft_params(const int* offsets, const unsigned int* ux, const unsigned int*
     const int nkeys = ntypes * p.nb;
     const size_t n_xoff = (size_t)n_frames * p.npairs * (nkeys + 1), n_rec = (size_t)n_frames * cap;
     const size_t n_corner = (size_t)n_frames * p.npairs * ntypes * 2;
-    const size_t need = n_xoff * sizeof(int) + 3 * n_rec * sizeof(unsigned int) + n_corner * sizeof(float) + 256;
+    const size_t need = n_xoff * sizeof(int) + 3 * n_rec * sizeof(unsigned int) + n_corner * sizeof(float) + n_rec * kTaps * sizeof(float) + 512;
     std::lock_guard<std::mutex> lk(g_mu);
     NufftWorkspace& w = g_ws[std::make_pair(rt::device(), owner)];
     if (need > w.bytes) {
@@ -529,6 +539,10 @@ int nufft_params(const int* offsets, const unsigned int* ux, const unsigned int*
     p.ry = p.rx + n_rec;
     p.rpar = p.ry + n_rec;
     p.corner = reinterpret_cast<float*>(p.rpar + n_rec);
+    // tap weights: 32 bytes per record, 16-byte aligned
+    uintptr_t wt = reinterpret_cast<uintptr_t>(p.corner + n_corner);
+    wt = (wt + 15) & ~(uintptr_t)15;
+    p.rwt = reinterpret_cast<float*>(wt);
     *out = p;
     return PSB_OK;
 }

@@ -3,7 +3,7 @@
 set -u
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-T=r2k
+T=r2m
 echo "== nufft parity"; timeout 1200 python -m pytest tests/test_gpu_parity.py -q -m gpu -x -s -k "nufft" 2>&1 | grep -E "rel-L2|passed|failed|Error|error|assert" | tail -30 | tee gpurun_out/${T}_pytest_nufft.log
 echo "== potential microbench, C4 geometry"
 for mode in 1 2; do PSB_SF_MODE=$mode PSB_GEOM=c4 PSB_LEVELS=1 PSB_PHASE=1 timeout 600 python tools/microbench_potential.py 8 64 2>&1 | tee -a gpurun_out/${T}_micro_pot.log; done
