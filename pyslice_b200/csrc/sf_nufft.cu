@@ -219,7 +219,7 @@ struct NufftCfg {
     static constexpr size_t kTileBytes = (size_t)kRows * W * sizeof(float2);
     static constexpr int kStage = W == 4 ? 1536 : 1024;      // records of one atom type staged in shared memory (more: read from L2)
     static constexpr size_t kEOffset = (kTileBytes + 3 * kStage * sizeof(unsigned int) + (T + 1) * sizeof(int) + (M / 2) * sizeof(float) + 15) / 16 * 16;
-    static constexpr size_t kSmem = kEOffset + (size_t)kStage * W * sizeof(float2) + (size_t)kStage * 8 * sizeof(float);
+    static constexpr size_t kSmem = kEOffset + (size_t)kStage * W * sizeof(float2) + (size_t)kStage * 8 * sizeof(float) + kThreads * sizeof(float2);
     static constexpr int kLogM = M == 2048 ? 11 : 10;
 };
 
@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     float* s_dec = reinterpret_cast<float*>(s_xoff + C::T + 1);                          // [nx]
     float2* s_e = reinterpret_cast<float2*>(smem_raw + C::kEOffset);                     // [kStage][W] exp(-2 pi i ky y) per record and column
     float* s_w = reinterpret_cast<float*>(s_e + (size_t)C::kStage * C::W);               // [kStage][8] tap weights
+    float2* s_dummy = reinterpret_cast<float2*>(s_w + (size_t)C::kStage * 8);            // [kThreads] where predicated-off taps land
     const int tid = threadIdx.x, c = tid % C::W, j = tid / C::W;
     constexpr int nx = M / 2;
     // persistent CTA: twiddles and the deconvolution table are loaded once, a contiguous range of (frame, pair, column
@@ -333,36 +334,84 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
 #pragma unroll
             for (int rr = 0; rr < 16; ++rr) tile[xc.at(16 * j + rr)] = make_float2(0.f, 0.f);
             __syncthreads();
-            // ---- spread: rows = fine cells, lane = (tap, column), one atom per trip
-            for (int bb = kBinsPerWarp * warp - 1; bb <= kBinsPerWarp * (warp + 1); ++bb) {
-                const int bin = (bb + C::T) % C::T;
-                const int i0 = s_xoff[bin], i1 = s_xoff[bin + 1];
-                for (int i = i0; i < i1; ++i) {
-                    // lane (tap k, column c): row, weight and phase factor of this record (staged, or from L2 beyond kStage)
-                    const bool staged = i < C::kStage;
-                    const unsigned int u = staged ? s_rx[i] : rx[r0 + i];
-                    float2 e;
-                    if (staged) {
+            // ---- spread: rows = fine cells, lane = (tap, column).  The warp's rows are split into two halves that it walks
+            //      as two independent streams in one instruction stream (a record is applied to the half its row falls
+            //      into, so the streams never touch the same cell): two dependency chains per trip instead of one, the
+            //      next trip's record prefetched before the read-modify-write, no branch in the body (lanes whose tap
+            //      falls outside the half add weight 0 to a private dummy cell).
+            {
+                constexpr int RS = RW / 2;                       // rows per stream
+                constexpr int kLogRS = kLogRW - 1;
+                constexpr int kBinsPerStream = RS / 16;
+                float2* dummy = s_dummy + tid;
+                int a0[2], a1[2];                                // staged record range of each stream: own bins + one bin either side
+                int h0[2] = {0, 0}, h1[2] = {0, 0};              // wrapped-around halo bin (first / last stream of the tile only)
+#pragma unroll
+                for (int st = 0; st < 2; ++st) {
+                    const int g = 2 * warp + st;                 // global stream index, rows [RS*g, RS*(g+1))
+                    int blo = kBinsPerStream * g - 1, bhi = kBinsPerStream * (g + 1);
+                    if (blo < 0) { h0[st] = s_xoff[C::T - 1]; h1[st] = s_xoff[C::T]; blo = 0; }
+                    if (bhi > C::T - 1) { h0[st] = s_xoff[0]; h1[st] = s_xoff[1]; bhi = C::T - 1; }
+                    a0[st] = s_xoff[blo];
+                    a1[st] = s_xoff[bhi + 1];
+                }
+                auto fetch = [&](int i, bool ok, unsigned int& u, float2& e, float& w, int k) {
+                    if (ok && i < C::kStage) {
+                        u = s_rx[i];
                         e = s_e[i * C::W + c];
-                    } else {
+                        w = s_w[i * kTaps + k];
+                    } else if (ok) {                              // beyond the staging area: from L2
+                        u = rx[r0 + i];
                         e = nyq_y ? make_float2(unit_phase_fast(p.ny / 2, ry[r0 + i]).x, 0.f) : unit_phase_fast(msy, ry[r0 + i]);
                         if (rpar[r0 + i]) e = make_float2(-e.y, e.x);
+                        w = rwt[(long long)(r0 + i) * kTaps + k];
+                    } else {
+                        u = 0; e = make_float2(0.f, 0.f); w = 0.f;
                     }
-                    const int cell = (int)(u >> kFracBits);
+                };
+                auto apply = [&](int g, unsigned int u, float2 e, float w, int k) {
+                    const int row = ((int)(u >> kFracBits) - 3 + k) & (M - 1);
+                    const bool own = (row >> kLogRS) == g;
+                    float2* cellp = own ? tile + xc.at(row) : dummy;
+                    const float ww = own ? w : 0.f;
+                    float2 acc = *cellp;
+                    acc.x = fmaf(ww, e.x, acc.x);
+                    acc.y = fmaf(ww, e.y, acc.y);
+                    *cellp = acc;
+                };
 #pragma unroll
-                    for (int q = 0; q < kTapsPerLane; ++q) {
-                        const int k = tap0 + kTapStride * q;
-                        const int row = (cell - 3 + k) & (M - 1);
-                        if ((row >> kLogRW) == warp) {
-                            const float w = staged ? s_w[i * kTaps + k] : rwt[(long long)(r0 + i) * kTaps + k];
-                            const int idx = xc.at(row);
-                            float2 g = tile[idx];
-                            g.x = fmaf(w, e.x, g.x);
-                            g.y = fmaf(w, e.y, g.y);
-                            tile[idx] = g;
-                        }
+                for (int q = 0; q < kTapsPerLane; ++q) {
+                    const int k = tap0 + kTapStride * q;
+                    const int n0 = a1[0] - a0[0], n1 = a1[1] - a0[1];
+                    const int trips = n0 > n1 ? n0 : n1;
+                    unsigned int u0, u1;
+                    float2 e0, e1;
+                    float w0, w1;
+                    fetch(a0[0], 0 < n0, u0, e0, w0, k);
+                    fetch(a0[1], 0 < n1, u1, e1, w1, k);
+                    for (int it = 0; it < trips; ++it) {
+                        unsigned int un0, un1;
+                        float2 en0, en1;
+                        float wn0, wn1;
+                        fetch(a0[0] + it + 1, it + 1 < n0, un0, en0, wn0, k);     // next trip's records: independent of the tile
+                        fetch(a0[1] + it + 1, it + 1 < n1, un1, en1, wn1, k);
+                        apply(2 * warp, u0, e0, w0, k);
+                        apply(2 * warp + 1, u1, e1, w1, k);
+                        __syncwarp();
+                        u0 = un0; e0 = en0; w0 = wn0;
+                        u1 = un1; e1 = en1; w1 = wn1;
                     }
-                    __syncwarp();
+                    // wrapped halo bins (first and last stream of the tile)
+#pragma unroll
+                    for (int st = 0; st < 2; ++st)
+                        for (int i = h0[st]; i < h1[st]; ++i) {
+                            unsigned int u;
+                            float2 e;
+                            float w;
+                            fetch(i, true, u, e, w, k);
+                            apply(2 * warp + st, u, e, w, k);
+                            __syncwarp();
+                        }
                 }
             }
             __syncthreads();
