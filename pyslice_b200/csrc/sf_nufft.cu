@@ -13,7 +13,7 @@
 // round-off of the sum itself.  Work per slice pair: atoms * 8 taps * ny complex FMAs + one 2 nx-point FFT per column and
 // atom type -- 8 x fewer flops than the direct sum at C4 and none of them atom-count dependent beyond the spreading.
 //
-//   K1  nufft_prep_kernel   one CTA per (slice pair, frame): orders the pair's atoms by (type, x bin of 16 fine cells) --
+//   K1  nufft_prep_kernel   one CTA per (slice pair, frame): orders the pair's atoms by (type, x bin of 8 fine cells) --
 //                           deterministically: ties keep list order -- and sums the (Nyquist, Nyquist) corner term.
 //   K2  nufft_cols_kernel   persistent, one CTA per SM walking (W adjacent ky columns, slice pair, frame) tiles: builds the G tile in shared memory
 //                           (thread (column, bin) spreads the atoms of its bin; even bins, then odd bins, so no two threads
@@ -60,7 +60,7 @@ struct NufftParams {
     int cap, nz, ntypes, nx, ny;
     int npairs;                 // slice pairs per frame
     int frame0, pair_begin, pair_count;     // K2: this chunk covers frames [frame0, frame0 + nf) x pairs [pair_begin, pair_begin + pair_count)
-    int nb, log_m;              // x bins per pair (= M / 16), log2(M)
+    int nb, log_m;              // x bins per pair (= M / 8), log2(M)
     // written by K1, read by K2
     int* xoff;                  // (F, npairs, ntypes*nb + 1) offsets into the pair's record range, by (type, bin)
     unsigned int* rx;           // (F, cap) records of a pair, ordered by (type, bin), list order inside
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256) nufft_prep_kernel(const NufftParams p) {
     const int begin = off[s0 * p.ntypes], end = off[s1 * p.ntypes], n = end - begin;
     const unsigned int* ux = p.ux + (long long)f * p.cap;
     const unsigned int* uy = p.uy + (long long)f * p.cap;
-    const int shift = 32 - p.log_m + 4;                                // bin = fine cell / 16
+    const int shift = 32 - p.log_m + 3;                                // bin = fine cell / 8
 
     auto seg_of = [&](int i) {                                         // list index -> segment (2 * ntypes candidates)
         int seg = s0 * p.ntypes;
@@ -218,8 +218,8 @@ struct NufftCfg {
     static constexpr int kRows = M + M / 16;         // padded
     static constexpr size_t kTileBytes = (size_t)kRows * W * sizeof(float2);
     static constexpr int kStage = W == 4 ? 1536 : 1024;      // records of one atom type staged in shared memory (more: read from L2)
-    static constexpr size_t kEOffset = (kTileBytes + 3 * kStage * sizeof(unsigned int) + (T + 1) * sizeof(int) + (M / 2) * sizeof(float) + 15) / 16 * 16;
-    static constexpr size_t kSmem = kEOffset + (size_t)kStage * W * sizeof(float2) + (size_t)kStage * 8 * sizeof(float) + kThreads * sizeof(float2);
+    static constexpr size_t kEOffset = (kTileBytes + 3 * kStage * sizeof(unsigned int) + (M / 8 + 1) * sizeof(int) + (M / 2) * sizeof(float) + 15) / 16 * 16;
+    static constexpr size_t kSmem = kEOffset + (size_t)kStage * W * sizeof(float2) + (size_t)kStage * 8 * sizeof(float);
     static constexpr int kLogM = M == 2048 ? 11 : 10;
 };
 
@@ -242,11 +242,10 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     unsigned int* s_rx = reinterpret_cast<unsigned int*>(smem_raw + C::kTileBytes);      // [kStage] records of the current (pair, type)
     unsigned int* s_ry = s_rx + C::kStage;
     unsigned int* s_rp = s_ry + C::kStage;
-    int* s_xoff = reinterpret_cast<int*>(s_rp + C::kStage);                              // [T + 1]
-    float* s_dec = reinterpret_cast<float*>(s_xoff + C::T + 1);                          // [nx]
+    int* s_xoff = reinterpret_cast<int*>(s_rp + C::kStage);                              // [M / 8 + 1]
+    float* s_dec = reinterpret_cast<float*>(s_xoff + M / 8 + 1);                         // [nx]
     float2* s_e = reinterpret_cast<float2*>(smem_raw + C::kEOffset);                     // [kStage][W] exp(-2 pi i ky y) per record and column
     float* s_w = reinterpret_cast<float*>(s_e + (size_t)C::kStage * C::W);               // [kStage][8] tap weights
-    float2* s_dummy = reinterpret_cast<float2*>(s_w + (size_t)C::kStage * 8);            // [kThreads] where predicated-off taps land
     const int tid = threadIdx.x, c = tid % C::W, j = tid / C::W;
     constexpr int nx = M / 2;
     // persistent CTA: twiddles and the deconvolution table are loaded once, a contiguous range of (frame, pair, column
@@ -255,24 +254,16 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     tw.load(p.tw, j);
     for (int i = tid; i < nx; i += C::kThreads) s_dec[i] = p.dec[i];
     const NufftXchg<M> xc{reinterpret_cast<cpx*>(tile), c};
-    const int nkeys = p.ntypes * C::T;
+    const int nkeys = p.ntypes * (M / 8);
     const int nseg = p.nz * p.ntypes;
     const int tiles_per_pair = p.ny / C::W;
     constexpr unsigned int kFracBits = 32 - C::kLogM;
     constexpr float kFracScale = 1.0f / (float)(1u << kFracBits);
-    // Spreading: warp w owns the fine rows [RW*w, RW*(w+1)) of the tile and walks the atoms whose 8 taps can reach them (its
-    // own x bins plus one bin on either side; the records are ordered by bin), one atom per trip: lane = (tap, column),
-    // so a trip is one weight, one phase-table read and one read-modify-write of the lane's cell.  No two warps ever touch
-    // the same cell, trips of one warp are ordered by __syncwarp, hence no barrier and no atomics inside the phase, and
-    // the sums are reproducible.  Row ranges are 128 (64) fine cells = 6.4 (3.2) A wide: a crystal's atomic planes spread
-    // evenly over the warps (per-bin ownership did not: 31 atoms in the fullest bin against a mean of 5).
+    // Spreading: warp w owns the fine rows [RW*w, RW*(w+1)) of the tile, 32 at a time (see the gather below)
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int RW = M / 16;                                    // rows per warp
     constexpr int kLogRW = C::kLogM - 4;
-    constexpr int kBinsPerWarp = RW / 16;
-    constexpr int kTapStride = 32 / C::W;                         // taps handled side by side: 8 (W = 4) or 4 (W = 8)
-    constexpr int kTapsPerLane = kTaps / kTapStride;              // 1 or 2
-    const int tap0 = lane / C::W;
+    constexpr int kBins = M / 8;                                  // x bins of 8 fine cells (the records are ordered by them)
     const int tile0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
     const int tile1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
     int staged_img = -1;
@@ -305,7 +296,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
             }
             // ---- stage this (pair, type)'s records and bin offsets (kept across the pair's column tiles when there is
             //      one atom type), clear the tile
-            const int r0 = xoff[z * C::T], r1 = xoff[(z + 1) * C::T];
+            const int r0 = xoff[z * (M / 8)], r1 = xoff[(z + 1) * (M / 8)];
             if (p.ntypes > 1 || staged_img != img) {
                 const int nstage = (r1 - r0) < C::kStage ? (r1 - r0) : C::kStage;
                 for (int i = tid; i < nstage; i += C::kThreads) {
@@ -315,7 +306,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                 }
                 for (int i = tid; i < nstage * 2; i += C::kThreads)
                     reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(rwt + (long long)r0 * kTaps)[i];
-                for (int i = tid; i <= C::T; i += C::kThreads) s_xoff[i] = xoff[z * C::T + i] - r0;
+                for (int i = tid; i <= M / 8; i += C::kThreads) s_xoff[i] = xoff[z * (M / 8) + i] - r0;
                 staged_img = img;
             }
             {   // phase factors of the staged records for this tile's columns (a record is used by up to two warps and eight taps)
@@ -331,88 +322,59 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                     s_e[q] = e;
                 }
             }
+            __syncthreads();                                     // phase factors staged
+            // ---- spread as a GATHER: lane = fine row, the warp's 32 consecutive rows walk the records whose taps can
+            //      reach them (bins of 8 cells around the rows; every lane reads the same record: broadcast loads), each
+            //      lane adds the tap that lands on its row -- w[record][row - cell + 3] -- times the record's phase factors
+            //      to its W column accumulators and stores the finished cells once.  No read-modify-write of shared
+            //      memory, no ordering between records beyond program order, no barrier: the earlier scatter forms were
+            //      bound by exactly those (profiles/r2_nufft_spread_history.txt).
+#pragma unroll 1
+            for (int pass = 0; pass < RW / 32; ++pass) {
+                const int r_first = RW * warp + 32 * pass;
+                const int r = r_first + lane;
+                float2 acc[C::W];
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) tile[xc.at(16 * j + rr)] = make_float2(0.f, 0.f);
-            __syncthreads();
-            // ---- spread: rows = fine cells, lane = (tap, column).  The warp's rows are split into two halves that it walks
-            //      as two independent streams in one instruction stream (a record is applied to the half its row falls
-            //      into, so the streams never touch the same cell): two dependency chains per trip instead of one, the
-            //      next trip's record prefetched before the read-modify-write, no branch in the body (lanes whose tap
-            //      falls outside the half add weight 0 to a private dummy cell).
-            {
-                constexpr int RS = RW / 2;                       // rows per stream
-                constexpr int kLogRS = kLogRW - 1;
-                constexpr int kBinsPerStream = RS / 16;
-                float2* dummy = s_dummy + tid;
-                int a0[2], a1[2];                                // staged record range of each stream: own bins + one bin either side
-                int h0[2] = {0, 0}, h1[2] = {0, 0};              // wrapped-around halo bin (first / last stream of the tile only)
+                for (int cc = 0; cc < C::W; ++cc) acc[cc] = make_float2(0.f, 0.f);
+                // records with cell in [r_first - 4, r_first + 35]: bins (r_first >> 3) - 1 .. (r_first >> 3) + 4
+                auto walk = [&](int i0, int i1) {
+                    for (int i = i0; i < i1; ++i) {
+                        const bool staged = i < C::kStage;
+                        const unsigned int u = staged ? s_rx[i] : rx[r0 + i];
+                        const int k = ((r - (int)(u >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;      // periodic distance, in taps
+                        if ((unsigned int)k < (unsigned int)kTaps) {
+                            const float w = staged ? s_w[i * kTaps + k] : rwt[(long long)(r0 + i) * kTaps + k];
+                            if (staged) {
 #pragma unroll
-                for (int st = 0; st < 2; ++st) {
-                    const int g = 2 * warp + st;                 // global stream index, rows [RS*g, RS*(g+1))
-                    int blo = kBinsPerStream * g - 1, bhi = kBinsPerStream * (g + 1);
-                    if (blo < 0) { h0[st] = s_xoff[C::T - 1]; h1[st] = s_xoff[C::T]; blo = 0; }
-                    if (bhi > C::T - 1) { h0[st] = s_xoff[0]; h1[st] = s_xoff[1]; bhi = C::T - 1; }
-                    a0[st] = s_xoff[blo];
-                    a1[st] = s_xoff[bhi + 1];
-                }
-                auto fetch = [&](int i, bool ok, unsigned int& u, float2& e, float& w, int k) {
-                    if (ok && i < C::kStage) {
-                        u = s_rx[i];
-                        e = s_e[i * C::W + c];
-                        w = s_w[i * kTaps + k];
-                    } else if (ok) {                              // beyond the staging area: from L2
-                        u = rx[r0 + i];
-                        e = nyq_y ? make_float2(unit_phase_fast(p.ny / 2, ry[r0 + i]).x, 0.f) : unit_phase_fast(msy, ry[r0 + i]);
-                        if (rpar[r0 + i]) e = make_float2(-e.y, e.x);
-                        w = rwt[(long long)(r0 + i) * kTaps + k];
-                    } else {
-                        u = 0; e = make_float2(0.f, 0.f); w = 0.f;
-                    }
-                };
-                auto apply = [&](int g, unsigned int u, float2 e, float w, int k) {
-                    const int row = ((int)(u >> kFracBits) - 3 + k) & (M - 1);
-                    const bool own = (row >> kLogRS) == g;
-                    float2* cellp = own ? tile + xc.at(row) : dummy;
-                    const float ww = own ? w : 0.f;
-                    float2 acc = *cellp;
-                    acc.x = fmaf(ww, e.x, acc.x);
-                    acc.y = fmaf(ww, e.y, acc.y);
-                    *cellp = acc;
-                };
+                                for (int cc = 0; cc < C::W; ++cc) {
+                                    const float2 e = s_e[i * C::W + cc];
+                                    acc[cc].x = fmaf(w, e.x, acc[cc].x);
+                                    acc[cc].y = fmaf(w, e.y, acc[cc].y);
+                                }
+                            } else {                             // beyond the staging area: phase factors on the fly
+                                const unsigned int v = ry[r0 + i];
+                                const bool par = rpar[r0 + i] != 0;
 #pragma unroll
-                for (int q = 0; q < kTapsPerLane; ++q) {
-                    const int k = tap0 + kTapStride * q;
-                    const int n0 = a1[0] - a0[0], n1 = a1[1] - a0[1];
-                    const int trips = n0 > n1 ? n0 : n1;
-                    unsigned int u0, u1;
-                    float2 e0, e1;
-                    float w0, w1;
-                    fetch(a0[0], 0 < n0, u0, e0, w0, k);
-                    fetch(a0[1], 0 < n1, u1, e1, w1, k);
-                    for (int it = 0; it < trips; ++it) {
-                        unsigned int un0, un1;
-                        float2 en0, en1;
-                        float wn0, wn1;
-                        fetch(a0[0] + it + 1, it + 1 < n0, un0, en0, wn0, k);     // next trip's records: independent of the tile
-                        fetch(a0[1] + it + 1, it + 1 < n1, un1, en1, wn1, k);
-                        apply(2 * warp, u0, e0, w0, k);
-                        apply(2 * warp + 1, u1, e1, w1, k);
-                        __syncwarp();
-                        u0 = un0; e0 = en0; w0 = wn0;
-                        u1 = un1; e1 = en1; w1 = wn1;
-                    }
-                    // wrapped halo bins (first and last stream of the tile)
-#pragma unroll
-                    for (int st = 0; st < 2; ++st)
-                        for (int i = h0[st]; i < h1[st]; ++i) {
-                            unsigned int u;
-                            float2 e;
-                            float w;
-                            fetch(i, true, u, e, w, k);
-                            apply(2 * warp + st, u, e, w, k);
-                            __syncwarp();
+                                for (int cc = 0; cc < C::W; ++cc) {
+                                    const int myc = my - c + cc;
+                                    const int msc = myc < (p.ny + 1) / 2 ? myc : myc - p.ny;
+                                    float2 e = ((p.ny % 2 == 0) && myc == p.ny / 2) ? make_float2(unit_phase_fast(p.ny / 2, v).x, 0.f)
+                                                                                     : unit_phase_fast(msc, v);
+                                    if (par) e = make_float2(-e.y, e.x);
+                                    acc[cc].x = fmaf(w, e.x, acc[cc].x);
+                                    acc[cc].y = fmaf(w, e.y, acc[cc].y);
+                                }
+                            }
                         }
-                }
+                    }
+                };
+                const int b_lo = (r_first >> 3) - 1, b_hi = (r_first >> 3) + 4;
+                if (b_lo < 0) walk(s_xoff[kBins - 1], s_xoff[kBins]);                 // wraps around the periodic axis
+                walk(s_xoff[b_lo < 0 ? 0 : b_lo], s_xoff[(b_hi > kBins - 1 ? kBins - 1 : b_hi) + 1]);
+                if (b_hi > kBins - 1) walk(s_xoff[0], s_xoff[1]);
+                float2* cells = tile + (r + (r >> 4)) * C::W;
+#pragma unroll
+                for (int cc = 0; cc < C::W; ++cc) cells[cc] = acc[cc];
             }
             __syncthreads();
             // ---- M-point transform along x, in place in the tile
@@ -518,7 +480,7 @@ int sf_mode() { return g_sf_mode.load(); }
 bool sf_nufft_supported(int ntypes, int nx, int ny) {
     if (nx != 512 && nx != 1024) return false;
     const int W = nx == 1024 ? 4 : 8;
-    return ny % W == 0 && ntypes * (nx / 8) <= kMaxKeys;
+    return ny % W == 0 && ntypes * (nx / 4) <= kMaxKeys;
 }
 
 // dense enough for the transform to beat the direct sum: atoms per slice pair and type (measured crossover)
@@ -556,7 +518,7 @@ int nufft_params(const int* offsets, const unsigned int* ux, const unsigned int*
     NufftParams p;
     std::memset(&p, 0, sizeof(p));
     p.offsets = offsets; p.ux = ux; p.uy = uy; p.cap = cap; p.nz = nz; p.ntypes = ntypes; p.nx = nx; p.ny = ny;
-    p.npairs = (nz + 1) / 2; p.nb = M / 16; p.log_m = M == 2048 ? 11 : 10;
+    p.npairs = (nz + 1) / 2; p.nb = M / 8; p.log_m = M == 2048 ? 11 : 10;
     p.ff = ff;
     int rc = dec_table(nx, &p.dec, owner);
     if (rc != PSB_OK) return rc;
