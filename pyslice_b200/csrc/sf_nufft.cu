@@ -337,36 +337,60 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
 #pragma unroll
                 for (int cc = 0; cc < C::W; ++cc) acc[cc] = make_float2(0.f, 0.f);
                 // records with cell in [r_first - 4, r_first + 35]: bins (r_first >> 3) - 1 .. (r_first >> 3) + 4
-                auto walk = [&](int i0, int i1) {
-                    for (int i = i0; i < i1; ++i) {
-                        const bool staged = i < C::kStage;
-                        const unsigned int u = staged ? s_rx[i] : rx[r0 + i];
-                        const int k = ((r - (int)(u >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;      // periodic distance, in taps
-                        if ((unsigned int)k < (unsigned int)kTaps) {
-                            const float w = staged ? s_w[i * kTaps + k] : rwt[(long long)(r0 + i) * kTaps + k];
-                            if (staged) {
+                // staged records: branch-free body, four records per trip (their loads are independent, so the shared-memory
+                // latency is paid once per four; a record whose taps miss this lane's row contributes weight 0)
+                auto staged4 = [&](int i) {
+                    float w[4];
 #pragma unroll
-                                for (int cc = 0; cc < C::W; ++cc) {
-                                    const float2 e = s_e[i * C::W + cc];
-                                    acc[cc].x = fmaf(w, e.x, acc[cc].x);
-                                    acc[cc].y = fmaf(w, e.y, acc[cc].y);
-                                }
-                            } else {                             // beyond the staging area: phase factors on the fly
-                                const unsigned int v = ry[r0 + i];
-                                const bool par = rpar[r0 + i] != 0;
+                    for (int q = 0; q < 4; ++q) {
+                        const int k = ((r - (int)(s_rx[i + q] >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;      // periodic distance, in taps
+                        const float ww = s_w[(i + q) * kTaps + (k & (kTaps - 1))];
+                        w[q] = (unsigned int)k < (unsigned int)kTaps ? ww : 0.f;
+                    }
 #pragma unroll
-                                for (int cc = 0; cc < C::W; ++cc) {
-                                    const int myc = my - c + cc;
-                                    const int msc = myc < (p.ny + 1) / 2 ? myc : myc - p.ny;
-                                    float2 e = ((p.ny % 2 == 0) && myc == p.ny / 2) ? make_float2(unit_phase_fast(p.ny / 2, v).x, 0.f)
-                                                                                     : unit_phase_fast(msc, v);
-                                    if (par) e = make_float2(-e.y, e.x);
-                                    acc[cc].x = fmaf(w, e.x, acc[cc].x);
-                                    acc[cc].y = fmaf(w, e.y, acc[cc].y);
-                                }
-                            }
+                    for (int q = 0; q < 4; ++q)
+#pragma unroll
+                        for (int cc = 0; cc < C::W; ++cc) {
+                            const float2 e = s_e[(i + q) * C::W + cc];
+                            acc[cc].x = fmaf(w[q], e.x, acc[cc].x);
+                            acc[cc].y = fmaf(w[q], e.y, acc[cc].y);
+                        }
+                };
+                auto staged1 = [&](int i) {
+                    const int k = ((r - (int)(s_rx[i] >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;
+                    const float ww = s_w[i * kTaps + (k & (kTaps - 1))];
+                    const float w = (unsigned int)k < (unsigned int)kTaps ? ww : 0.f;
+#pragma unroll
+                    for (int cc = 0; cc < C::W; ++cc) {
+                        const float2 e = s_e[i * C::W + cc];
+                        acc[cc].x = fmaf(w, e.x, acc[cc].x);
+                        acc[cc].y = fmaf(w, e.y, acc[cc].y);
+                    }
+                };
+                auto unstaged = [&](int i) {                     // beyond the staging area: from L2, phase factors on the fly
+                    const int k = ((r - (int)(rx[r0 + i] >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;
+                    if ((unsigned int)k < (unsigned int)kTaps) {
+                        const float w = rwt[(long long)(r0 + i) * kTaps + k];
+                        const unsigned int v = ry[r0 + i];
+                        const bool par = rpar[r0 + i] != 0;
+#pragma unroll
+                        for (int cc = 0; cc < C::W; ++cc) {
+                            const int myc = my - c + cc;
+                            const int msc = myc < (p.ny + 1) / 2 ? myc : myc - p.ny;
+                            float2 e = ((p.ny % 2 == 0) && myc == p.ny / 2) ? make_float2(unit_phase_fast(p.ny / 2, v).x, 0.f)
+                                                                             : unit_phase_fast(msc, v);
+                            if (par) e = make_float2(-e.y, e.x);
+                            acc[cc].x = fmaf(w, e.x, acc[cc].x);
+                            acc[cc].y = fmaf(w, e.y, acc[cc].y);
                         }
                     }
+                };
+                auto walk = [&](int i0, int i1) {
+                    const int i1s = i1 < C::kStage ? i1 : C::kStage;
+                    int i = i0;
+                    for (; i + 4 <= i1s; i += 4) staged4(i);
+                    for (; i < i1s; ++i) staged1(i);
+                    for (; i < i1; ++i) unstaged(i);
                 };
                 const int b_lo = (r_first >> 3) - 1, b_hi = (r_first >> 3) + 4;
                 if (b_lo < 0) walk(s_xoff[kBins - 1], s_xoff[kBins]);                 // wraps around the periodic axis
