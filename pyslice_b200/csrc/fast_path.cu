@@ -162,6 +162,12 @@ constexpr bool row_mode_steps(int mode) { return mode == R_STEP || mode == R_STE
 #define PSB_ROW_WARPS_PHASE 16
 #endif
 
+// phases of the slice (R_STEP_PHASE) loaded straight into registers with streaming loads at the start of a unit (1) instead
+// of TMA -> landing buffer -> LDS (0): 8 B per pixel less through the L1 / shared-memory pipe, 16 more live registers
+#ifndef PSB_ROW_PHASE_LDG
+#define PSB_ROW_PHASE_LDG 0
+#endif
+
 template <int N, int MODE = 0>
 struct RowCfg {
     static constexpr int T = N / 16;               // threads per line
@@ -254,7 +260,7 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
             else
                 bulk_g2s(land_psi, p.psi + (long long)unit * C::kLand, C::kBytes, mb_psi);
         }
-        if (row_mode_steps(MODE) && want_t) {
+        if (row_mode_steps(MODE) && want_t && !(MODE == R_STEP_PHASE && PSB_ROW_PHASE_LDG)) {
             mbar_expect_tx(mb_t + tb, C::kTBytes);
             bulk_g2s_hint(land_t + tb * C::kTLand, t_rows(unit), C::kTBytes, mb_t + tb, stream_once);
         }
@@ -282,18 +288,27 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
         if constexpr (row_mode_steps(MODE)) {
             cpx v[16];
             const float* ltf = reinterpret_cast<const float*>(land_t) + c * N + j;      // R_STEP_PHASE: float rows
+            float tph[16];
+            if constexpr (MODE == R_STEP_PHASE && PSB_ROW_PHASE_LDG) {                  // in flight during the inverse transform
+                const float* gph = reinterpret_cast<const float*>(t_rows(u)) + c * N + j;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) tph[e] = __ldcs(gph + e * C::T);
+            }
             // psi[x, ky] -> IFFT_y -> * t[x, y]
             fast::line_fft<N, +1>(
                 [&](int e) { return lp[e * C::T]; },
                 [&](int e, cpx a) {
-                    if constexpr (MODE == R_STEP_PHASE) v[e] = fast::cmulp(a, cis1(ltf[e * C::T]));
+                    if constexpr (MODE == R_STEP_PHASE && PSB_ROW_PHASE_LDG) v[e] = fast::cmulp(a, cis1(tph[e]));
+                    else if constexpr (MODE == R_STEP_PHASE) v[e] = fast::cmulp(a, cis1(ltf[e * C::T]));
                     else v[e] = fast::cmulp(a, lt[e * C::T]);
                 },
                 tw, j, xc, 0,
                 [&]() {
                     if (lane == 0 && next) issue(un, true, false);
                 },
-                [&]() { mbar_wait(mb_t + tb, t_parity); });
+                [&]() {
+                    if constexpr (!(MODE == R_STEP_PHASE && PSB_ROW_PHASE_LDG)) mbar_wait(mb_t + tb, t_parity);
+                });
             // -> FFT_y -> global
             cpx* dst = reinterpret_cast<cpx*>(p.psi) + (long long)u * C::kLand + c * N + j;
             fast::line_fft<N, -1>([&](int e) { return v[e]; }, [&](int e, cpx a) { dst[e * C::T] = a; }, tw, j, xc, 0, [&]() {
@@ -353,6 +368,10 @@ struct ColPassParams {
 #define PSB_COL_XBUFS 2
 #endif
 constexpr int kColXBufs = PSB_COL_XBUFS;
+// Px[kx] of the thread's 16 line positions in registers for the whole kernel (1) instead of 16 shared-memory loads per tile (0)
+#ifndef PSB_COL_PX_REGS
+#define PSB_COL_PX_REGS 1      // measured: +2.6 % at 256^2, +2 % at 512^2 (profiles/r2t_slice_step_variants.txt)
+#endif
 constexpr int kColCtasPerSm = kColXBufs == 1 ? 3 : 2;
 
 // 1024-point columns: 512 threads and 8-column tiles in one CTA per SM (default), or 256 threads and 4-column tiles in
@@ -438,6 +457,12 @@ __global__ void __launch_bounds__(ColCfg<N>::kThreads, ColCfg<N>::kCtasPerSm) fa
     }
     const cpx* gpx = reinterpret_cast<const cpx*>(p.px);
     const cpx* gpy = reinterpret_cast<const cpx*>(p.py);
+    cpx pxr[16];
+    constexpr bool kPxRegs = PSB_COL_PX_REGS && N < 1024;      // 1024-point columns have no registers to spare
+    if constexpr (MODE == C_PROPAGATE && kPxRegs) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) pxr[e] = gpx[tid / C::W + e * C::T];
+    }
 
     const int c = tid % C::W, j = tid / C::W;
     fast::Twiddles<N> tw;
@@ -475,7 +500,8 @@ __global__ void __launch_bounds__(ColCfg<N>::kThreads, ColCfg<N>::kCtasPerSm) fa
             const cpx pyc = C::kTablesInSmem ? spy[col] : __ldg(gpy + col);
             fast::line_fft<N, -1>([&](int e) { return fast::cmulp(lp[e * C::T * C::W], pyc); },
                                   [&](int e, cpx a) {
-                                      v[e] = fast::cmulp(a, C::kTablesInSmem ? spx[j + e * C::T] : __ldg(gpx + j + e * C::T));
+                                      if constexpr (kPxRegs) v[e] = fast::cmulp(a, pxr[e]);
+                                      else v[e] = fast::cmulp(a, C::kTablesInSmem ? spx[j + e * C::T] : __ldg(gpx + j + e * C::T));
                                   },
                                   tw, j, xc, 0);
             xc.next_c0 = -1;

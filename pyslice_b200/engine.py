@@ -30,6 +30,7 @@ SCRATCH_BYTES = 64 << 20
 # per-device batch workspaces of the calculators (multislice/calculators.py: run()), kept so that consecutive runs and
 # consecutive calculators of one geometry see the same device addresses (CUDA-graph replay in libpsb keys on them)
 WORKSPACES = {}
+_FF_CACHE = {}      # (device, grid, types) -> form-factor table on the device (make_plan)
 
 
 class PhaseTimer:
@@ -195,7 +196,15 @@ def make_plan(xs, ys, zs, atom_kinds: Sequence, eV: float, device=None) -> Slice
     type_idx = np.array([lut[z] for z in Z.tolist()], dtype=np.int32)
     lo, hi, dz = hostmath.slice_bounds(zs)
     kxs, kys = hostmath.kgrid(xs, ys)
-    ff = hostmath.form_factor_table(kxs, kys, type_Z).astype(np.float32)
+    # Kirkland form factors on the k grid: a pure function of (grid, atom types), 6-40 ms of NumPy per setup() at 256^2 ...
+    # 1024^2 -- kept per device for the next calculator of the same geometry (a few entries, oldest dropped)
+    ff_key = (str(device), nx, ny, float(xs[1] - xs[0]), float(ys[1] - ys[0]), tuple(type_Z))
+    ff_dev = _FF_CACHE.get(ff_key)
+    if ff_dev is None:
+        ff_dev = torch.from_numpy(hostmath.form_factor_table(kxs, kys, type_Z).astype(np.float32)).to(device)
+        if len(_FF_CACHE) >= 4:
+            _FF_CACHE.pop(next(iter(_FF_CACHE)))
+        _FF_CACHE[ff_key] = ff_dev
     lam = hostmath.wavelength(eV)
     px, py = hostmath.propagator_tables(kxs, kys, lam, dz)
     px = px / (nx * ny)
@@ -203,7 +212,7 @@ def make_plan(xs, ys, zs, atom_kinds: Sequence, eV: float, device=None) -> Slice
         device=device, xs=xs, ys=ys, zs=zs, nx=nx, ny=ny, nz=nz, dx=float(xs[1] - xs[0]), dy=float(ys[1] - ys[0]),
         dz=dz, eV=eV, wavelength=lam, sigma=hostmath.interaction_sigma(eV), type_Z=type_Z,
         type_idx=torch.from_numpy(type_idx).to(device), lo=torch.from_numpy(lo).to(device),
-        hi=torch.from_numpy(hi).to(device), formfactors=torch.from_numpy(ff).to(device),
+        hi=torch.from_numpy(hi).to(device), formfactors=ff_dev,
         prop_x=_c64(px, device), prop_y=_c64(py, device), kxs=kxs, kys=kys)
 
 
