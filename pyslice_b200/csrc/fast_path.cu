@@ -372,7 +372,6 @@ constexpr int kColXBufs = PSB_COL_XBUFS;
 #ifndef PSB_COL_PX_REGS
 #define PSB_COL_PX_REGS 1      // measured: +2.6 % at 256^2, +2 % at 512^2 (profiles/r2t_slice_step_variants.txt)
 #endif
-constexpr int kColCtasPerSm = kColXBufs == 1 ? 3 : 2;
 
 // 1024-point columns: 512 threads and 8-column tiles in one CTA per SM (default), or 256 threads and 4-column tiles in
 // two CTAs per SM (-DPSB_COL1024_THREADS=256)
@@ -384,18 +383,38 @@ constexpr int kColCtasPerSm = kColXBufs == 1 ? 3 : 2;
 #ifndef PSB_COL512_THREADS
 #define PSB_COL512_THREADS 256
 #endif
+// 256-point columns: 256 threads and 16-column tiles in two CTAs per SM (default), or 128 threads and 8-column tiles in four
+#ifndef PSB_COL256_THREADS
+#define PSB_COL256_THREADS 256
+#endif
+#ifndef PSB_COL1024_TABLES_SMEM
+#define PSB_COL1024_TABLES_SMEM 1
+#endif
 
-template <int N>
+// The inverse-only pass of the potential build does one transform per tile (ncu r2w: issue slots 29 % busy, 4.5
+// long-scoreboard stalls per issue with 2 CTAs per SM).  1: one exchange buffer, 3 CTAs per SM -- measured equal
+// (2.178 against 2.174 ms per 16 frames of C2, profiles/r2x_potential_chunk_sweep.txt), so the propagate pass's shape stays
+#ifndef PSB_COL_INV_3CTAS
+#define PSB_COL_INV_3CTAS 0
+#endif
+
+enum ColMode { C_PROPAGATE = 0, C_INVERSE = 1 };
+
+template <int N, int MODE>
 struct ColCfg {
     static constexpr int T = N / 16;
-    static constexpr int kThreads = N == 1024 ? PSB_COL1024_THREADS : (N == 512 ? PSB_COL512_THREADS : 256);
-    static constexpr int kCtasPerSm = N == 1024 ? (kThreads == 512 ? 1 : 2) : ((N == 512 && kThreads == 512) ? 1 : kColCtasPerSm);
+    static constexpr int kXBufs = (MODE == C_INVERSE && N < 1024 && PSB_COL_INV_3CTAS) ? 1 : kColXBufs;
+    static constexpr int kThreads = N == 1024 ? PSB_COL1024_THREADS : (N == 512 ? PSB_COL512_THREADS : PSB_COL256_THREADS);
+    static constexpr int kCtasPerSm = N == 1024 ? (kThreads == 512 ? 1 : 2)
+                                    : ((N == 512 && kThreads == 512) ? 1 : (kXBufs == 1 ? 3 : 2) * (N == 256 ? 256 / kThreads : 1));
     static constexpr int W = kThreads / T;                            // columns per tile: 16 (N=256), 8 (N=512, 1024), 4 (1024, 256 threads)
     static constexpr int kPadRows = (W < 16) ? N / 16 : 0;            // keeps narrow rows conflict-free
     static constexpr int kLand = N * W;                               // float2 (32 KB; 64 KB for N = 1024)
     static constexpr int kX = (N + kPadRows) * W;
-    static constexpr bool kTablesInSmem = N < 1024;                   // Px, Py staged per CTA (1024: read through L1)
-    static constexpr size_t kSmem = (size_t)(kLand + kColXBufs * kX + (kTablesInSmem ? N : 0)) * sizeof(float2) + 2 * sizeof(uint64_t);      // + NY*8 for Py, added at launch
+    // Px, Py staged per CTA.  1024 with one 512-thread CTA per SM: 64 + 2 x 68 + 16 KB = 216 KB still fits (ncu r2v: with the
+    // tables read through L1 the kernel's top stall was long-scoreboard, 4.1 per issue); two 256-thread CTAs: through L1
+    static constexpr bool kTablesInSmem = MODE == C_PROPAGATE && (N < 1024 || (PSB_COL1024_TABLES_SMEM && kThreads == 512));
+    static constexpr size_t kSmem = (size_t)(kLand + kXBufs * kX + (kTablesInSmem ? N : 0)) * sizeof(float2) + 2 * sizeof(uint64_t);      // + NY*8 for Py, added at launch
     static constexpr int kBoxRows = 256;                              // TMA box limit per dimension
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
     static constexpr size_t smem_for(int ny) { return kSmem + (kTablesInSmem ? (size_t)ny * sizeof(float2) : 0); }
@@ -403,8 +422,9 @@ struct ColCfg {
 
 // Exchange policy of the column pass: two alternating buffers, one CTA barrier per exchange.  The first
 // barrier of a tile doubles as the "landing buffer is free" point: thread 0 then issues the next tile's TMA.
-template <int N>
+template <int N, int MODE>
 struct ColXchg {
+    using C = ColCfg<N, MODE>;
     cpx* b0;
     cpx* b1;
     int c;
@@ -413,34 +433,32 @@ struct ColXchg {
     cpx* land;
     int next_c0, next_r0;        // tensor coordinates of the next tile; next_c0 < 0: nothing to prefetch
     int hook_i;                  // index of the tile's first exchange
-    __device__ __forceinline__ cpx* buf(int i) const { return (kColXBufs == 2 && (i & 1)) ? b1 : b0; }
+    __device__ __forceinline__ cpx* buf(int i) const { return (C::kXBufs == 2 && (i & 1)) ? b1 : b0; }
     __device__ __forceinline__ int at(int q) const {
-        return (ColCfg<N>::W < 16 ? q + (q >> 4) : q) * ColCfg<N>::W + c;
+        return (C::W < 16 ? q + (q >> 4) : q) * C::W + c;
     }
     __device__ __forceinline__ void after_store(int i) const {
         __syncthreads();
         if (i == hook_i && next_c0 >= 0 && threadIdx.x == 0) {      // first barrier of the tile
-            mbar_expect_tx(mb, ColCfg<N>::kBytes);
+            mbar_expect_tx(mb, C::kBytes);
 #pragma unroll
-            for (int h = 0; h < N / ColCfg<N>::kBoxRows; ++h)
-                tensor2d_g2s(land + h * ColCfg<N>::kBoxRows * ColCfg<N>::W, map, next_c0, next_r0 + h * ColCfg<N>::kBoxRows, mb);
+            for (int h = 0; h < N / C::kBoxRows; ++h)
+                tensor2d_g2s(land + h * C::kBoxRows * C::W, map, next_c0, next_r0 + h * C::kBoxRows, mb);
         }
     }
     __device__ __forceinline__ void after_load(int) const {
-        if (kColXBufs == 1) __syncthreads();
+        if (C::kXBufs == 1) __syncthreads();
     }
     __device__ __forceinline__ void mid_sync(int) const { __syncthreads(); }
 };
 
-enum ColMode { C_PROPAGATE = 0, C_INVERSE = 1 };
-
 template <int N, int NY, int MODE>
-__global__ void __launch_bounds__(ColCfg<N>::kThreads, ColCfg<N>::kCtasPerSm) fast_cols_kernel(const __grid_constant__ CUtensorMap tmap, const ColPassParams p) {
-    using C = ColCfg<N>;
+__global__ void __launch_bounds__(ColCfg<N, MODE>::kThreads, ColCfg<N, MODE>::kCtasPerSm) fast_cols_kernel(const __grid_constant__ CUtensorMap tmap, const ColPassParams p) {
+    using C = ColCfg<N, MODE>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     cpx* land = reinterpret_cast<cpx*>(smem_raw);
     cpx* xb0 = land + C::kLand;
-    cpx* xb1 = xb0 + (kColXBufs - 1) * C::kX;
+    cpx* xb1 = xb0 + (C::kXBufs - 1) * C::kX;
     cpx* spx = xb1 + C::kX;
     cpx* spy = spx + (C::kTablesInSmem ? N : 0);
     uint64_t* mb = reinterpret_cast<uint64_t*>(spy + (C::kTablesInSmem ? NY : 0));
@@ -473,7 +491,7 @@ __global__ void __launch_bounds__(ColCfg<N>::kThreads, ColCfg<N>::kCtasPerSm) fa
 
     long long tile = blockIdx.x;
     const long long G = gridDim.x;
-    ColXchg<N> xc{xb0, xb1, c, &tmap, mb, land, -1, 0, 0};
+    ColXchg<N, MODE> xc{xb0, xb1, c, &tmap, mb, land, -1, 0, 0};
     if (tile < p.n_tiles && tid == 0) {
         mbar_expect_tx(mb, C::kBytes);
 #pragma unroll
@@ -579,7 +597,7 @@ int rows_go(const RowPassParams& p, cudaStream_t s) {
 
 template <int N, int NY, int MODE>
 int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const float2* tw, cudaStream_t s) {
-    using C = ColCfg<N>;
+    using C = ColCfg<N, MODE>;
     static rt::PerDeviceOnce once;
     int rc0 = once.run([] { return ensure_smem(fast_cols_kernel<N, NY, MODE>, C::smem_for(NY), "fast column pass"); });
     if (rc0 != PSB_OK) return rc0;

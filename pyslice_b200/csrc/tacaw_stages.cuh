@@ -3,6 +3,7 @@
 // can run a tile's stage sequence thread by thread and check index arithmetic, twiddle selection and the output
 // permutation against numpy without a GPU.
 #pragma once
+#include "fast_fft.cuh"
 #include "psb_common.cuh"
 
 #include <cstdlib>
@@ -12,49 +13,46 @@ namespace tw {
 
 constexpr int kMaxFactors = 16;
 
-PSB_HD float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }      // a * (-i)
+using fast::cpx;
 
-// forward R-point DFTs in registers (W_R = exp(-2 pi i / R))
-PSB_HD void dft2(float2* x) {
-    const float2 a = x[0], b = x[1];
-    x[0] = cadd(a, b);
-    x[1] = csub(a, b);
+// forward R-point DFTs in registers (W_R = exp(-2 pi i / R)) on packed complex values: every complex add is one FADD2,
+// every real-constant scaling one FMUL2 / FFMA2, the (y, -x) rotations ride on the operand swizzle of the packed
+// instructions.  (The scalar float2 version of round 1 issued 77 instructions per element at T = 100 and the kernel was
+// issue-bound: 70 % of the issue slots busy at 0.61 of the copy bandwidth, ncu r2v.)
+PSB_D cpx both(float v) { return fast::c_make(v, v); }
+PSB_D void dft2(cpx* x) {
+    const cpx a = x[0], b = x[1];
+    x[0] = fast::add2(a, b);
+    x[1] = fast::sub2(a, b);
 }
-PSB_HD void dft3(float2* x) {
+PSB_D void dft3(cpx* x) {
     const float c = -0.5f, s = 0.86602540378443865f;
-    const float2 t1 = cadd(x[1], x[2]), t2 = csub(x[1], x[2]);
-    const float2 m = make_float2(x[0].x + c * t1.x, x[0].y + c * t1.y);
-    const float2 r = make_float2(s * t2.y, -s * t2.x);                 // -i*s*(x1 - x2)
-    x[0] = cadd(x[0], t1);
-    x[1] = cadd(m, r);
-    x[2] = csub(m, r);
+    const cpx t1 = fast::add2(x[1], x[2]), t2 = fast::sub2(x[1], x[2]);
+    const cpx m = fast::fma2(t1, both(c), x[0]);
+    const cpx u = fast::mul2(t2, both(s));
+    x[0] = fast::add2(x[0], t1);
+    x[1] = fast::sub_ib(m, u);          // m - i*s*(x1 - x2)
+    x[2] = fast::add_ib(m, u);
 }
-PSB_HD void dft4(float2* x) {
-    const float2 s02 = cadd(x[0], x[2]), d02 = csub(x[0], x[2]);
-    const float2 s13 = cadd(x[1], x[3]), d13 = mul_mi(csub(x[1], x[3]));
-    x[0] = cadd(s02, s13);
-    x[2] = csub(s02, s13);
-    x[1] = cadd(d02, d13);
-    x[3] = csub(d02, d13);
-}
-PSB_HD void dft5(float2* x) {
+PSB_D void dft4(cpx* x) { fast::radix4<-1>(x[0], x[1], x[2], x[3]); }
+PSB_D void dft5(cpx* x) {
     const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;      // cos(2 pi/5), cos(4 pi/5)
     const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;       // sin(2 pi/5), sin(4 pi/5)
-    const float2 a1 = cadd(x[1], x[4]), b1 = csub(x[1], x[4]);
-    const float2 a2 = cadd(x[2], x[3]), b2 = csub(x[2], x[3]);
-    const float2 m1 = make_float2(x[0].x + c1 * a1.x + c2 * a2.x, x[0].y + c1 * a1.y + c2 * a2.y);
-    const float2 m2 = make_float2(x[0].x + c2 * a1.x + c1 * a2.x, x[0].y + c2 * a1.y + c1 * a2.y);
-    const float2 r1 = make_float2(s1 * b1.y + s2 * b2.y, -(s1 * b1.x + s2 * b2.x));    // -i*(s1 b1 + s2 b2)
-    const float2 r2 = make_float2(s2 * b1.y - s1 * b2.y, -(s2 * b1.x - s1 * b2.x));    // -i*(s2 b1 - s1 b2)
-    x[0] = cadd(x[0], cadd(a1, a2));
-    x[1] = cadd(m1, r1);
-    x[4] = csub(m1, r1);
-    x[2] = cadd(m2, r2);
-    x[3] = csub(m2, r2);
+    const cpx a1 = fast::add2(x[1], x[4]), b1 = fast::sub2(x[1], x[4]);
+    const cpx a2 = fast::add2(x[2], x[3]), b2 = fast::sub2(x[2], x[3]);
+    const cpx m1 = fast::fma2(a2, both(c2), fast::fma2(a1, both(c1), x[0]));
+    const cpx m2 = fast::fma2(a2, both(c1), fast::fma2(a1, both(c2), x[0]));
+    const cpx u1 = fast::fma2(b2, both(s2), fast::mul2(b1, both(s1)));      // s1 b1 + s2 b2
+    const cpx u2 = fast::fma2(b2, both(-s1), fast::mul2(b1, both(s2)));     // s2 b1 - s1 b2
+    x[0] = fast::add2(x[0], fast::add2(a1, a2));
+    x[1] = fast::sub_ib(m1, u1);
+    x[4] = fast::add_ib(m1, u1);
+    x[2] = fast::sub_ib(m2, u2);
+    x[3] = fast::add_ib(m2, u2);
 }
 
 template <int R>
-PSB_HD void dft(float2* x) {
+PSB_D void dft(cpx* x) {
     if constexpr (R == 2) dft2(x);
     else if constexpr (R == 3) dft3(x);
     else if constexpr (R == 4) dft4(x);
@@ -67,8 +65,12 @@ PSB_HD void dft(float2* x) {
 // |.|^2 straight to global memory, so an element crosses shared memory twice per middle stage and once at each end.
 
 template <int R, int PX, int kThreads>
-PSB_D void first_stage(unsigned tid, float2* data, const float2* PSB_RESTRICT src, long long stride_frame, bool live,
-                                            const float2* PSB_RESTRICT tw, int T) {
+PSB_D void first_stage(unsigned tid, float2* data_, const float2* PSB_RESTRICT src_, long long stride_frame, bool live,
+                       const float2* PSB_RESTRICT tw_, int T) {
+    cpx* data = reinterpret_cast<cpx*>(data_);
+    const cpx* PSB_RESTRICT src = reinterpret_cast<const cpx*>(src_);
+    const cpx* PSB_RESTRICT tw = reinterpret_cast<const cpx*>(tw_);
+    const cpx zero = fast::c_make(0.f, 0.f);
     const int sub = T / R;
     const int px = tid % PX;
     constexpr int step = kThreads / PX;
@@ -77,61 +79,76 @@ PSB_D void first_stage(unsigned tid, float2* data, const float2* PSB_RESTRICT sr
     // asks of an SM (ncu r1j: long-scoreboard stalls 4.0 per issue, 0.61 of the copy bandwidth).
     int n = tid / PX;
     for (; n + step < sub; n += 2 * step) {
-        float2 x[R], y[R];
+        cpx x[R], y[R];
 #pragma unroll
-        for (int i = 0; i < R; ++i) x[i] = live ? src[(long long)(n + i * sub) * stride_frame] : make_float2(0.f, 0.f);
+        for (int i = 0; i < R; ++i) x[i] = live ? src[(long long)(n + i * sub) * stride_frame] : zero;
 #pragma unroll
-        for (int i = 0; i < R; ++i) y[i] = live ? src[(long long)(n + step + i * sub) * stride_frame] : make_float2(0.f, 0.f);
+        for (int i = 0; i < R; ++i) y[i] = live ? src[(long long)(n + step + i * sub) * stride_frame] : zero;
         dft<R>(x);
         data[n * PX + px] = x[0];
 #pragma unroll
-        for (int k = 1; k < R; ++k) data[(k * sub + n) * PX + px] = cmul(x[k], __ldg(&tw[n * k]));
+        for (int k = 1; k < R; ++k) data[(k * sub + n) * PX + px] = fast::cmulp(x[k], __ldg(&tw[n * k]));
         dft<R>(y);
         data[(n + step) * PX + px] = y[0];
 #pragma unroll
-        for (int k = 1; k < R; ++k) data[(k * sub + n + step) * PX + px] = cmul(y[k], __ldg(&tw[(n + step) * k]));
+        for (int k = 1; k < R; ++k) data[(k * sub + n + step) * PX + px] = fast::cmulp(y[k], __ldg(&tw[(n + step) * k]));
     }
     for (; n < sub; n += step) {
-        float2 x[R];
+        cpx x[R];
 #pragma unroll
-        for (int i = 0; i < R; ++i) x[i] = live ? src[(long long)(n + i * sub) * stride_frame] : make_float2(0.f, 0.f);
+        for (int i = 0; i < R; ++i) x[i] = live ? src[(long long)(n + i * sub) * stride_frame] : zero;
         dft<R>(x);
         data[n * PX + px] = x[0];
 #pragma unroll
-        for (int k = 1; k < R; ++k) data[(k * sub + n) * PX + px] = cmul(x[k], __ldg(&tw[n * k]));
+        for (int k = 1; k < R; ++k) data[(k * sub + n) * PX + px] = fast::cmulp(x[k], __ldg(&tw[n * k]));
     }
 }
 
 template <int R, int PX, int kThreads>
-PSB_D void mid_stage(unsigned tid, float2* data, const float2* PSB_RESTRICT tw, int T, int B) {
+PSB_D void mid_stage(unsigned tid, float2* data_, const float2* PSB_RESTRICT tw_, int T, int B) {
+    cpx* data = reinterpret_cast<cpx*>(data_);
+    const cpx* PSB_RESTRICT tw = reinterpret_cast<const cpx*>(tw_);
     const int sub = B / R;
     const int tstep = T / B;
     const int px = tid % PX;
     const int n_bf = T / R;
-    for (int bi = tid / PX; bi < n_bf; bi += kThreads / PX) {
-        const int q = bi / sub, n = bi - q * sub;
-        float2* base = data + (q * B + n) * PX + px;
-        float2 x[R];
+    constexpr int step = kThreads / PX;
+    // butterfly bi = q * sub + n; (q, n) advance with the loop instead of a division per butterfly
+    int bi = tid / PX;
+    int q = bi / sub, n = bi - q * sub;
+    const int dq = step / sub, dn = step - dq * sub;
+    for (; bi < n_bf; bi += step) {
+        cpx* base = data + (q * B + n) * PX + px;
+        cpx x[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) x[i] = base[i * sub * PX];
         dft<R>(x);
         base[0] = x[0];
+        const int tn = n * tstep;
 #pragma unroll
-        for (int k = 1; k < R; ++k) base[k * sub * PX] = cmul(x[k], __ldg(&tw[n * k * tstep]));
+        for (int k = 1; k < R; ++k) base[k * sub * PX] = fast::cmulp(x[k], __ldg(&tw[tn * k]));
+        n += dn;
+        q += dq;
+        if (n >= sub) {
+            n -= sub;
+            ++q;
+        }
     }
 }
 
 // kFromGlobal: the transform has a single stage (T = R), inputs come from global memory as well
 template <int R, int PX, int kThreads, bool kFromGlobal>
-PSB_D void last_stage(unsigned tid, const float2* data, const float2* PSB_RESTRICT src, long long stride_frame, bool live,
-                                           const int* PSB_RESTRICT perm, float* PSB_RESTRICT dst, long long npix, int T) {
+PSB_D void last_stage(unsigned tid, const float2* data_, const float2* PSB_RESTRICT src_, long long stride_frame, bool live,
+                      const int* PSB_RESTRICT perm, float* PSB_RESTRICT dst, long long npix, int T) {
+    const cpx* data = reinterpret_cast<const cpx*>(data_);
+    const cpx* PSB_RESTRICT src = reinterpret_cast<const cpx*>(src_);
     const int px = tid % PX;
     const int n_bf = T / R;
     for (int q = tid / PX; q < n_bf; q += kThreads / PX) {
-        float2 x[R];
+        cpx x[R];
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-            if (kFromGlobal) x[i] = live ? src[(long long)i * stride_frame] : make_float2(0.f, 0.f);
+            if (kFromGlobal) x[i] = live ? src[(long long)i * stride_frame] : fast::c_make(0.f, 0.f);
             else x[i] = data[(q * R + i) * PX + px];
         }
         dft<R>(x);
@@ -140,7 +157,8 @@ PSB_D void last_stage(unsigned tid, const float2* data, const float2* PSB_RESTRI
         for (int k = 0; k < R; ++k) {
             const int pos = q * R + k;
             // position 0 holds X[0] = T * mean: psi - <psi>_t differs from psi in this bin only (and is 0 there)
-            const float v = pos == 0 ? 0.f : x[k].x * x[k].x + x[k].y * x[k].y;
+            const cpx sq = fast::mul2(x[k], x[k]);
+            const float v = pos == 0 ? 0.f : fast::c_re(sq) + fast::c_im(sq);
             dst[(long long)__ldg(&perm[pos]) * npix] = v;
         }
     }

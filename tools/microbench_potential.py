@@ -13,7 +13,7 @@ sizes = [int(x) for x in sys.argv[2:]] or [32, 64, 96]
 if os.environ.get("PSB_GEOM") == "c4":          # 38 400 atoms, 1024 x 1024 x 123
     traj = synthetic.silicon_trajectory(cells=(20, 20, 12), a=5.1175, n_frames=F, seed=3, displacement="phonon")
 else:
-    traj = synthetic.silicon_trajectory(cells=(5, 5, 50), a=5.11, n_frames=F, seed=1, displacement="phonon")
+    traj = synthetic.silicon_trajectory(cells=(5, 5, int(os.environ.get("PSB_ZCELLS", "50"))), a=5.11, n_frames=F, seed=1, displacement="phonon")
 xs, ys, zs, *_ = hostmath.grid_from_box(traj.box_matrix)
 plan = engine.make_plan(xs, ys, zs, traj.atom_types.tolist(), 100e3)
 pos = torch.from_numpy(traj.positions).cuda()
