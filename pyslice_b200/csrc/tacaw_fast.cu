@@ -25,6 +25,7 @@
 #include "tacaw_stages.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -50,7 +51,7 @@ struct TwFastParams {
 };
 
 // kThreads: 256 when several tiles fit one SM's shared memory, 1024 when a tile (long series) has the SM to itself
-template <int PX, int kThreads>
+template <int PX, int kThreads, int BIG>
 __global__ void __launch_bounds__(kThreads) tacaw_fast_kernel(const TwFastParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2* data = reinterpret_cast<float2*>(smem_raw);             // [T][PX]
@@ -116,21 +117,39 @@ int get_tables(int T, TwTables* out, cudaStream_t s) {
     return PSB_OK;
 }
 
-template <int PX, int kThreads>
-int go(const TwFastParams& p, int n_probes, cudaStream_t s) {
+inline int radix_class(const int* fac, int nfac) {      // 0: radices up to 5, 1: up to 10, 2: up to 20
+    int c = 0;
+    for (int i = 0; i < nfac; ++i) c = fac[i] > 10 ? 2 : (fac[i] > 5 && c < 1 ? 1 : c);
+    return c;
+}
+
+template <int PX, int kThreads, int BIG>
+int go_as(const TwFastParams& p, int n_probes, cudaStream_t s) {
     const size_t smem = (size_t)p.T * PX * sizeof(float2);
     static std::atomic<size_t> smem_set[64];          // per device ordinal (the attribute is per device), zero-initialised
     const int d = rt::device() & 63;
     if (smem > smem_set[d].load(std::memory_order_acquire)) {
-        cudaError_t e = cudaFuncSetAttribute(tacaw_fast_kernel<PX, kThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tacaw_fast_kernel<PX, kThreads, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return fail(PSB_ERR_CUDA, std::string("tacaw fast path: ") + cudaGetErrorString(e));
         smem_set[d].store(smem, std::memory_order_release);
     }
     const long long tiles = (p.npix + PX - 1) / PX;
-    tacaw_fast_kernel<PX, kThreads><<<dim3((unsigned)tiles, (unsigned)n_probes), kThreads, smem, s>>>(p);
+    tacaw_fast_kernel<PX, kThreads, BIG><<<dim3((unsigned)tiles, (unsigned)n_probes), kThreads, smem, s>>>(p);
     ++launch_counter();
     return rt::check("tacaw fast launch");
 }
+
+template <int PX, int kThreads>
+int go(const TwFastParams& p, int n_probes, cudaStream_t s) {
+    // radix-10 / 20 butterflies want up to 127 registers: a whole-SM tile runs them with 512 threads instead of 1024
+    constexpr int kBigThreads = kThreads > 512 ? 512 : kThreads;
+    switch (radix_class(p.fac, p.nfac)) {
+        case 2: return go_as<PX, kBigThreads, 2>(p, n_probes, s);
+        case 1: return go_as<PX, kBigThreads, 1>(p, n_probes, s);
+        default: return go_as<PX, kThreads, 0>(p, n_probes, s);
+    }
+}
+
 
 }  // namespace
 
@@ -161,7 +180,12 @@ int launch_tacaw_fast(const float2* wf, long long stride_probe, long long stride
     if (n_probes == 0 || npix == 0) return PSB_OK;
     const bool one_per_sm = whole_sm(n_frames);      // 32 warps on a tile that has the SM to itself
     switch (pick_px(n_frames)) {
-        case 64: return go<64, 256>(p, n_probes, s);
+        case 64: {
+            // radix-10 stages of T = 100 k: T/10 butterflies x 64 pixels split evenly over 320 threads but not over 256
+            const long long items = (long long)(n_frames / 10) * 64;
+            if (tb.fac[0] == 10 && items % 320 == 0 && items % 256 != 0) return go_as<64, 320, 1>(p, n_probes, s);
+            return go<64, 256>(p, n_probes, s);
+        }
         case 32: return go<32, 256>(p, n_probes, s);
         case 16: return go<16, 256>(p, n_probes, s);
         case 8: return one_per_sm ? go<8, 1024>(p, n_probes, s) : go<8, 256>(p, n_probes, s);

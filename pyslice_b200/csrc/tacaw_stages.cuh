@@ -52,11 +52,42 @@ PSB_D void dft5(cpx* x) {
 }
 
 template <int R>
+PSB_D void dft(cpx* x);
+
+// N1 x N2 points with coprime factors by the prime-factor (Good-Thomas) mapping: input n = N2 n1 + N1 n2, output
+// k = I1 k1 + I2 k2 (mod N) with I1 = N2 (N2^-1 mod N1), I2 = N1 (N1^-1 mod N2) -- no twiddles between the two layers, and
+// with everything unrolled the index maps are register renaming.  A stage of radix 10 or 20 replaces two stages of
+// radix 2/4 and 5: one trip through shared memory, one barrier and one set of twiddle multiplies less per element.
+template <int N1, int N2, int I1, int I2>
+PSB_D void dft_pfa(cpx* x) {
+    constexpr int N = N1 * N2;
+    cpx y[N2][N1];
+#pragma unroll
+    for (int n2 = 0; n2 < N2; ++n2) {
+#pragma unroll
+        for (int n1 = 0; n1 < N1; ++n1) y[n2][n1] = x[(N2 * n1 + N1 * n2) % N];
+        dft<N1>(y[n2]);
+    }
+#pragma unroll
+    for (int k1 = 0; k1 < N1; ++k1) {
+        cpx z[N2];
+#pragma unroll
+        for (int n2 = 0; n2 < N2; ++n2) z[n2] = y[n2][k1];
+        dft<N2>(z);
+#pragma unroll
+        for (int k2 = 0; k2 < N2; ++k2) x[(I1 * k1 + I2 * k2) % N] = z[k2];
+    }
+}
+
+template <int R>
 PSB_D void dft(cpx* x) {
     if constexpr (R == 2) dft2(x);
     else if constexpr (R == 3) dft3(x);
     else if constexpr (R == 4) dft4(x);
-    else dft5(x);
+    else if constexpr (R == 5) dft5(x);
+    else if constexpr (R == 10) dft_pfa<2, 5, 5, 6>(x);
+    else dft_pfa<4, 5, 5, 16>(x);
+    static_assert(R == 2 || R == 3 || R == 4 || R == 5 || R == 10 || R == 20, "radix");
 }
 
 // Stage s of the decimation in frequency splits every block of B elements into R sub-blocks of B / R:
@@ -78,6 +109,7 @@ PSB_D void first_stage(unsigned tid, float2* data_, const float2* PSB_RESTRICT s
     // butterfly per trip a CTA kept R*kThreads*8 bytes in flight -- about half of what the HBM latency-bandwidth product
     // asks of an SM (ncu r1j: long-scoreboard stalls 4.0 per issue, 0.61 of the copy bandwidth).
     int n = tid / PX;
+    if constexpr (R <= 5)          // a radix-10 / 20 butterfly has that many loads in flight by itself
     for (; n + step < sub; n += 2 * step) {
         cpx x[R], y[R];
 #pragma unroll
@@ -164,26 +196,49 @@ PSB_D void last_stage(unsigned tid, const float2* data_, const float2* PSB_RESTR
     }
 }
 
+// BIG: 0 = the kernel instance with radices up to 5, 1 = also radix 10, 2 = also radix 20 (more registers each; separate
+// instances so that frame counts without such factors keep their occupancy)
 #define PSB_TW_DISPATCH(R_, CALL)                 \
     do {                                          \
-        if ((R_) == 5) { constexpr int R = 5; CALL; }      \
+        if (BIG >= 2 && (R_) == 20) { constexpr int R = BIG >= 2 ? 20 : 2; CALL; }      \
+        else if (BIG >= 1 && (R_) == 10) { constexpr int R = BIG >= 1 ? 10 : 2; CALL; } \
+        else if ((R_) == 5) { constexpr int R = 5; CALL; }      \
         else if ((R_) == 4) { constexpr int R = 4; CALL; } \
         else if ((R_) == 3) { constexpr int R = 3; CALL; } \
         else { constexpr int R = 2; CALL; }                \
     } while (0)
 
 // ---- host-side planning ------------------------------------------------------------------------------
-inline bool factorise(int T, int* fac, int* nfac) {
+inline bool factorise_with(int T, const int* radices, int nr, int* fac, int* nfac) {
     int n = 0, r = T;
-    const int radices[4] = {5, 4, 3, 2};
-    for (int R : radices)
-        while (r % R == 0 && r > 1) {
+    for (int i = 0; i < nr; ++i)
+        while (r % radices[i] == 0 && r > 1) {
             if (n == kMaxFactors) return false;
-            fac[n++] = R;
-            r /= R;
+            fac[n++] = radices[i];
+            r /= radices[i];
         }
     *nfac = n;
     return r == 1 && n > 0;
+}
+// fewest stages first; among equals the plan without radix 20 (fewer registers, better balanced stages):
+// 20 -> {20}, 100 -> {10, 10}, 500 -> {10, 10, 5}, 2000 -> {20, 10, 10}
+inline bool factorise(int T, int* fac, int* nfac) {
+    const int r20[6] = {20, 10, 5, 4, 3, 2}, r10[5] = {10, 5, 4, 3, 2};
+    int f10[kMaxFactors], n10 = 0;
+    if (!factorise_with(T, r10, 5, f10, &n10)) return false;
+    if (factorise_with(T, r20, 6, fac, nfac) && *nfac < n10) {
+        // one radix 20 is enough when the rest folds into tens: {20, 20, 5} -> {20, 10, 10}
+        for (int i = 0; i + 2 < *nfac; ++i)
+            if (fac[i] == 20 && fac[i + 1] == 20 && fac[*nfac - 1] == 5) {
+                fac[i + 1] = 10;
+                fac[*nfac - 1] = 10;
+                break;
+            }
+        return true;
+    }
+    for (int i = 0; i < n10; ++i) fac[i] = f10[i];
+    *nfac = n10;
+    return true;
 }
 
 // storage position pos = k1*(T/R1) + k2*(T/(R1 R2)) + ... holds X[k], k = k1 + R1*(k2 + R2*(...)); fftshift: k -> (k + T/2) % T

@@ -15,6 +15,7 @@ namespace {
 
 template <int PX, int NT>
 int tile(int T, long long npix, const float2* wf, long long stride_frame, float* out) {
+    constexpr int BIG = 2;
     int fac[kMaxFactors], nfac = 0;
     if (!factorise(T, fac, &nfac)) return -2;
     std::vector<float2> twd(T);
