@@ -155,6 +155,10 @@ constexpr bool row_mode_steps(int mode) { return mode == R_STEP || mode == R_STE
 #ifndef PSB_ROW_TBUFS
 #define PSB_ROW_TBUFS 1
 #endif
+// the same for the phase-format slice step: its rows are half the size, so two buffers still leave room for 16 warps
+#ifndef PSB_ROW_TBUFS_PHASE
+#define PSB_ROW_TBUFS_PHASE 1
+#endif
 
 // warps per CTA of the phase-format slice step (R_STEP_PHASE): its transmission landing buffer is half the size, which
 // leaves room for 20 warps (5 per scheduler) in shared memory and, at <= 96 registers, in the register file
@@ -174,7 +178,7 @@ struct RowCfg {
     static constexpr int kGroupThreads = T > 32 ? T : 32;      // threads that share buffers and synchronise: a warp, or a warp pair (N = 1024)
     static constexpr int LPW = kGroupThreads / T;  // lines per group (unit of work)
     static constexpr int NP = N + N / 16;          // padded exchange pitch
-    static constexpr int kTBufs = (MODE == 0) ? PSB_ROW_TBUFS : 1;
+    static constexpr int kTBufs = (MODE == 0) ? PSB_ROW_TBUFS : ((MODE == 3) ? PSB_ROW_TBUFS_PHASE : 1);
     static constexpr int kWarps = (MODE == 3) ? PSB_ROW_WARPS_PHASE : ((kTBufs == 1) ? 16 : 12);
     static constexpr int kThreads = 32 * kWarps;
     static constexpr int kGroups = kThreads / kGroupThreads;
@@ -287,7 +291,7 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
         const cpx* lt = land_t + tb * C::kTLand + c * N + j;
         if constexpr (row_mode_steps(MODE)) {
             cpx v[16];
-            const float* ltf = reinterpret_cast<const float*>(land_t) + c * N + j;      // R_STEP_PHASE: float rows
+            const float* ltf = reinterpret_cast<const float*>(land_t + tb * C::kTLand) + c * N + j;      // R_STEP_PHASE: float rows
             float tph[16];
             if constexpr (MODE == R_STEP_PHASE && PSB_ROW_PHASE_LDG) {                  // in flight during the inverse transform
                 const float* gph = reinterpret_cast<const float*>(t_rows(u)) + c * N + j;

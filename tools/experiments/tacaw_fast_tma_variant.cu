@@ -3,6 +3,8 @@
 //     C3 quarter 4.94 against 4.90 TB/s for the plain kernel with the same radix-10 stages, C2 2.4 against 3.0,
 //     T = 2000 1.46 against 2.24 (profiles/r2z_tacaw_history.txt): bytes in flight were not what held the kernel back,
 //     the balance of its stages was (320 threads for 640 butterfly-pixels per stage: 5.61 TB/s);
+//   * a single-buffer form of the same kernel for whole-SM tiles (T = 2000): 1.375 against 1.374 ms -- load and transform of a
+//     128 KB tile stay serialised either way, and shared memory has no room for a second one;
 //   * L2 prefetch of the next whole-SM tile (PSB_TACAW_AHEAD): T = 2000 1.72 against 1.40 ms.
 // TACAW time-axis transform for frame counts of the form 2^a 3^b 5^c (every BASELINE.json configuration: 20, 100, 500,
 // 2000) -- reference: src/postprocessing/tacaw_data.py:61-106,
