@@ -391,6 +391,12 @@ constexpr int kColXBufs = PSB_COL_XBUFS;
 #ifndef PSB_COL256_THREADS
 #define PSB_COL256_THREADS 256
 #endif
+// 1024-point columns, alternative shape (1): two 256-thread CTAs per SM, each landing 8-column tiles (64-byte rows for the
+// tensor copy) and transforming them as two halves of 4 columns through ONE exchange buffer -- two independent CTAs fill
+// each other's barrier bubbles where the single 512-thread CTA idles (ncu r2v: issue slots 34 % busy)
+#ifndef PSB_COL1024_HALVES
+#define PSB_COL1024_HALVES 0
+#endif
 #ifndef PSB_COL1024_TABLES_SMEM
 #define PSB_COL1024_TABLES_SMEM 1
 #endif
@@ -407,21 +413,25 @@ enum ColMode { C_PROPAGATE = 0, C_INVERSE = 1 };
 template <int N, int MODE>
 struct ColCfg {
     static constexpr int T = N / 16;
-    static constexpr int kXBufs = (MODE == C_INVERSE && N < 1024 && PSB_COL_INV_3CTAS) ? 1 : kColXBufs;
-    static constexpr int kThreads = N == 1024 ? PSB_COL1024_THREADS : (N == 512 ? PSB_COL512_THREADS : PSB_COL256_THREADS);
+    static constexpr int kHalves = (N == 1024 && PSB_COL1024_HALVES) ? 2 : 1;      // column groups of a tile transformed one after the other
+    static constexpr int kXBufs = (kHalves == 2 || (MODE == C_INVERSE && N < 1024 && PSB_COL_INV_3CTAS)) ? 1 : kColXBufs;
+    static constexpr int kThreads = N == 1024 ? (kHalves == 2 ? 256 : PSB_COL1024_THREADS) : (N == 512 ? PSB_COL512_THREADS : PSB_COL256_THREADS);
     static constexpr int kCtasPerSm = N == 1024 ? (kThreads == 512 ? 1 : 2)
                                     : ((N == 512 && kThreads == 512) ? 1 : (kXBufs == 1 ? 3 : 2) * (N == 256 ? 256 / kThreads : 1));
-    static constexpr int W = kThreads / T;                            // columns per tile: 16 (N=256), 8 (N=512, 1024), 4 (1024, 256 threads)
+    static constexpr int W = kThreads / T;                            // columns transformed together: 16 (N=256), 8 (N=512, 1024), 4 (1024, 256 threads)
+    static constexpr int WL = W * kHalves;                            // columns per tile (landing buffer, tensor-copy box)
     static constexpr int kPadRows = (W < 16) ? N / 16 : 0;            // keeps narrow rows conflict-free
-    static constexpr int kLand = N * W;                               // float2 (32 KB; 64 KB for N = 1024)
+    static constexpr int kLand = N * WL;                              // float2 (32 KB; 64 KB for N = 1024)
     static constexpr int kX = (N + kPadRows) * W;
     // Px, Py staged per CTA.  1024 with one 512-thread CTA per SM: 64 + 2 x 68 + 16 KB = 216 KB still fits (ncu r2v: with the
-    // tables read through L1 the kernel's top stall was long-scoreboard, 4.1 per issue); two 256-thread CTAs: through L1
-    static constexpr bool kTablesInSmem = MODE == C_PROPAGATE && (N < 1024 || (PSB_COL1024_TABLES_SMEM && kThreads == 512));
+    // tables read through L1 the kernel's top stall was long-scoreboard, 4.1 per issue); two 256-thread CTAs: through L1;
+    // the two-halves shape: Px staged, Py (one value per thread and half) through L1
+    static constexpr bool kTablesInSmem = MODE == C_PROPAGATE && (N < 1024 || kHalves == 2 || (PSB_COL1024_TABLES_SMEM && kThreads == 512));
+    static constexpr bool kPyInSmem = kTablesInSmem && kHalves == 1;
     static constexpr size_t kSmem = (size_t)(kLand + kXBufs * kX + (kTablesInSmem ? N : 0)) * sizeof(float2) + 2 * sizeof(uint64_t);      // + NY*8 for Py, added at launch
     static constexpr int kBoxRows = 256;                              // TMA box limit per dimension
     static constexpr uint32_t kBytes = kLand * sizeof(float2);
-    static constexpr size_t smem_for(int ny) { return kSmem + (kTablesInSmem ? (size_t)ny * sizeof(float2) : 0); }
+    static constexpr size_t smem_for(int ny) { return kSmem + (kPyInSmem ? (size_t)ny * sizeof(float2) : 0); }
 };
 
 // Exchange policy of the column pass: two alternating buffers, one CTA barrier per exchange.  The first
@@ -447,7 +457,7 @@ struct ColXchg {
             mbar_expect_tx(mb, C::kBytes);
 #pragma unroll
             for (int h = 0; h < N / C::kBoxRows; ++h)
-                tensor2d_g2s(land + h * C::kBoxRows * C::W, map, next_c0, next_r0 + h * C::kBoxRows, mb);
+                tensor2d_g2s(land + h * C::kBoxRows * C::WL, map, next_c0, next_r0 + h * C::kBoxRows, mb);
         }
     }
     __device__ __forceinline__ void after_load(int) const {
@@ -465,7 +475,7 @@ __global__ void __launch_bounds__(ColCfg<N, MODE>::kThreads, ColCfg<N, MODE>::kC
     cpx* xb1 = xb0 + (C::kXBufs - 1) * C::kX;
     cpx* spx = xb1 + C::kX;
     cpx* spy = spx + (C::kTablesInSmem ? N : 0);
-    uint64_t* mb = reinterpret_cast<uint64_t*>(spy + (C::kTablesInSmem ? NY : 0));
+    uint64_t* mb = reinterpret_cast<uint64_t*>(spy + (C::kPyInSmem ? NY : 0));
 
     const int tid = threadIdx.x;
     if (tid == 0) {
@@ -475,7 +485,8 @@ __global__ void __launch_bounds__(ColCfg<N, MODE>::kThreads, ColCfg<N, MODE>::kC
     pdl_trigger();
     if constexpr (MODE == C_PROPAGATE && C::kTablesInSmem) {
         for (int i = tid; i < N; i += C::kThreads) spx[i] = reinterpret_cast<const cpx*>(p.px)[i];
-        for (int i = tid; i < NY; i += C::kThreads) spy[i] = reinterpret_cast<const cpx*>(p.py)[i];
+        if constexpr (C::kPyInSmem)
+            for (int i = tid; i < NY; i += C::kThreads) spy[i] = reinterpret_cast<const cpx*>(p.py)[i];
     }
     const cpx* gpx = reinterpret_cast<const cpx*>(p.px);
     const cpx* gpy = reinterpret_cast<const cpx*>(p.py);
@@ -491,7 +502,7 @@ __global__ void __launch_bounds__(ColCfg<N, MODE>::kThreads, ColCfg<N, MODE>::kC
     tw.load(p.tw, j);
     __syncthreads();
     pdl_wait();          // constant tables above, images below
-    constexpr int kTilesPerImg = NY / C::W;
+    constexpr int kTilesPerImg = NY / C::WL;
 
     long long tile = blockIdx.x;
     const long long G = gridDim.x;
@@ -500,41 +511,42 @@ __global__ void __launch_bounds__(ColCfg<N, MODE>::kThreads, ColCfg<N, MODE>::kC
         mbar_expect_tx(mb, C::kBytes);
 #pragma unroll
         for (int h = 0; h < N / C::kBoxRows; ++h)
-            tensor2d_g2s(land + h * C::kBoxRows * C::W, &tmap, (int)(tile % kTilesPerImg) * C::W,
+            tensor2d_g2s(land + h * C::kBoxRows * C::WL, &tmap, (int)(tile % kTilesPerImg) * C::WL,
                          (int)(tile / kTilesPerImg) * N + h * C::kBoxRows, mb);
     }
     for (uint32_t it = 0; tile < p.n_tiles; tile += G, ++it) {
         const long long nt = tile + G;
-        if (nt < p.n_tiles) {
-            xc.next_c0 = (int)(nt % kTilesPerImg) * C::W;
-            xc.next_r0 = (int)(nt / kTilesPerImg) * N;
-        } else {
-            xc.next_c0 = -1;
-        }
+        const int next_c0 = nt < p.n_tiles ? (int)(nt % kTilesPerImg) * C::WL : -1;
+        xc.next_r0 = nt < p.n_tiles ? (int)(nt / kTilesPerImg) * N : 0;
         mbar_wait(mb, it & 1u);
-        const cpx* lp = land + j * C::W + c;
-        cpx* dst = reinterpret_cast<cpx*>(p.psi) + (tile / kTilesPerImg) * ((long long)N * NY) + (tile % kTilesPerImg) * C::W + j * NY + c;
-        if constexpr (MODE == C_PROPAGATE) {
-            cpx v[16];
-            // * Py[ky] -> FFT_x -> * Px[kx] -> IFFT_x
-            xc.hook_i = 0;
-            const int col = (int)(tile % kTilesPerImg) * C::W + c;
-            const cpx pyc = C::kTablesInSmem ? spy[col] : __ldg(gpy + col);
-            fast::line_fft<N, -1>([&](int e) { return fast::cmulp(lp[e * C::T * C::W], pyc); },
-                                  [&](int e, cpx a) {
-                                      if constexpr (kPxRegs) v[e] = fast::cmulp(a, pxr[e]);
-                                      else v[e] = fast::cmulp(a, C::kTablesInSmem ? spx[j + e * C::T] : __ldg(gpx + j + e * C::T));
-                                  },
-                                  tw, j, xc, 0);
-            xc.next_c0 = -1;
-            fast::line_fft<N, +1>([&](int e) { return v[e]; }, [&](int e, cpx a) { dst[e * C::T * NY] = a; }, tw, j, xc,
-                                  fast::exchanges<N>());
-        } else {
-            // one transform per tile: alternate the exchange buffer between tiles so a single barrier per
-            // exchange still orders the reuse (N = 512 already alternates inside the transform)
-            xc.hook_i = fast::exchanges<N>() == 1 ? (int)(it & 1u) : 0;
-            fast::line_fft<N, +1>([&](int e) { return lp[e * C::T * C::W]; }, [&](int e, cpx a) { dst[e * C::T * NY] = a; }, tw, j,
-                                  xc, xc.hook_i);
+#pragma unroll 1
+        for (int half = 0; half < C::kHalves; ++half) {
+            // the landing buffer goes back to the tensor copy once its last columns have been read
+            xc.next_c0 = half == C::kHalves - 1 ? next_c0 : -1;
+            const int col0 = (int)(tile % kTilesPerImg) * C::WL + half * C::W;
+            const cpx* lp = land + j * C::WL + half * C::W + c;
+            cpx* dst = reinterpret_cast<cpx*>(p.psi) + (tile / kTilesPerImg) * ((long long)N * NY) + col0 + j * NY + c;
+            if constexpr (MODE == C_PROPAGATE) {
+                cpx v[16];
+                // * Py[ky] -> FFT_x -> * Px[kx] -> IFFT_x
+                xc.hook_i = 0;
+                const cpx pyc = C::kPyInSmem ? spy[col0 + c] : __ldg(gpy + col0 + c);
+                fast::line_fft<N, -1>([&](int e) { return fast::cmulp(lp[e * C::T * C::WL], pyc); },
+                                      [&](int e, cpx a) {
+                                          if constexpr (kPxRegs) v[e] = fast::cmulp(a, pxr[e]);
+                                          else v[e] = fast::cmulp(a, C::kTablesInSmem ? spx[j + e * C::T] : __ldg(gpx + j + e * C::T));
+                                      },
+                                      tw, j, xc, 0);
+                xc.next_c0 = -1;
+                fast::line_fft<N, +1>([&](int e) { return v[e]; }, [&](int e, cpx a) { dst[e * C::T * NY] = a; }, tw, j, xc,
+                                      fast::exchanges<N>());
+            } else {
+                // one transform per tile: alternate the exchange buffer between tiles so a single barrier per
+                // exchange still orders the reuse (N = 512 already alternates inside the transform)
+                xc.hook_i = fast::exchanges<N>() == 1 ? (int)(it & 1u) : 0;
+                fast::line_fft<N, +1>([&](int e) { return lp[e * C::T * C::WL]; }, [&](int e, cpx a) { dst[e * C::T * NY] = a; }, tw, j,
+                                      xc, xc.hook_i);
+            }
         }
     }
 }
@@ -612,14 +624,14 @@ int cols_go(float2* psi, int n_img, const float2* px, const float2* py, const fl
     static thread_local float2* map_psi = nullptr;
     static thread_local int map_img = -1;
     if (map_psi != psi || map_img != n_img) {
-        int rc = encode_cols_map(&map, psi, (long long)n_img * N, NY, C::W, C::kBoxRows);
+        int rc = encode_cols_map(&map, psi, (long long)n_img * N, NY, C::WL, C::kBoxRows);
         if (rc != PSB_OK) return rc;
         map_psi = psi;
         map_img = n_img;
     }
     ColPassParams p;
     p.psi = psi; p.px = px; p.py = py; p.tw = tw;
-    p.n_tiles = (long long)n_img * (NY / C::W);
+    p.n_tiles = (long long)n_img * (NY / C::WL);
     const long long slots = (long long)C::kCtasPerSm * rt::sm_count();
     const int grid = (int)(p.n_tiles < slots ? p.n_tiles : slots);
     cudaError_t e = pdl_launch(fast_cols_kernel<N, NY, MODE>, dim3(grid), dim3(C::kThreads), C::smem_for(NY), s, map, p);

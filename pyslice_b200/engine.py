@@ -20,6 +20,10 @@ from ctypes import sizeof as C_sizeof
 # transmission stack streams through L2 with an evict-first hint, so ~3/5 of L2 can hold psi
 # (measured: 148 images of 256^2 = 74 MB still resident, 185 = 93 MB not; profiles/r1e notes).
 PSI_BATCH_BYTES = 80 << 20
+# 1024-point grids: one image is 8 MB and a batch that fills the persistent grids never fits L2, so psi streams from HBM
+# whatever the batch; then larger batches only amortise launch ramps and tails (measured 9 / 16 / 24 / 37 images:
+# 110 / 112 / 115 / 119 k slice-steps/s, profiles/r2ad_batch_sweep.txt; 256 and 512 points lose 13-18 % past L2).
+PSI_BATCH_BYTES_STREAMING = 320 << 20
 # Upper bound for the transmission-function buffer of one frame batch.
 T_BATCH_BYTES = 48 << 30
 # Workspace of the potential build (slice-paired spectra): chunks of this size flow through the three
@@ -489,7 +493,7 @@ def batch_sizes(plan: SlicePlan, n_probes: int, n_frames: int):
     stays bounded, the image count fills the persistent slice-step grids, and batches are balanced."""
     img = plan.nx * plan.ny * 8
     per_frame_t = plan.nz * img
-    max_imgs = max(1, PSI_BATCH_BYTES // img)
+    max_imgs = max(1, (PSI_BATCH_BYTES_STREAMING if plan.nx * plan.ny >= 1024 * 1024 else PSI_BATCH_BYTES) // img)
     slots = (1 if plan.nx >= 1024 else 2) * _sm_count()          # CTAs of the column pass that run side by side
     tiles_per_img = max(1, plan.ny // (8 if plan.nx >= 512 else 16))
     if n_probes >= max_imgs:
