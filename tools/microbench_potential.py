@@ -27,6 +27,8 @@ for fast in [int(x) for x in os.environ.get('PSB_LEVELS', '2,1,0').split(',')]:
     engine.set_fast_path(fast)
     for mb in sizes:
         engine.SCRATCH_BYTES = mb << 20
+        if os.environ.get('PSB_CHUNK_PAIRS') == '1':          # sizes are slice-pair images per chunk instead of MB
+            engine.SCRATCH_BYTES = mb * 8 * plan.nx * plan.ny
         for _ in range(2):
             engine.build_transmission(plan, pos, out=tphase if PHASE and fast > 0 else tbuf, phase=PHASE and fast > 0)
         torch.cuda.synchronize()
