@@ -311,7 +311,8 @@ def cpu_baseline(wl, name):
 
 
 L2_NOTE = ("GPU arm: inputs larger than L2, no explicit flush -- every timed step streams the positions and a multi-GB "
-           "transmission stack per frame batch through HBM; only the psi batch (<= 80 MB) is L2-resident by design")
+           "transmission stack per frame batch through HBM; only the psi batch (<= 80 MB) is L2-resident by design "
+           "(1024-point grids: psi streams from HBM too, batches of up to 320 MB)")
 
 
 def config_block(wl, name, world, counts, A, P):
