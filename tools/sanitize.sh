@@ -27,6 +27,12 @@ for box, n, pp, ap in cases:
     tac = TACAWData(calc.run())
     s = tac.spectrum()
     assert np.isfinite(s).all()
+# time transform alone: radix-10 / 20 prime-factor stages (T = 20 single stage, 100 = 10 x 10 on 320-thread tiles, 500, 2000 on a
+# whole-SM tile), ragged pixel counts
+for P, T, npix in [(2, 20, 70), (2, 100, 4 * 64 + 9), (1, 500, 40), (1, 2000, 20), (1, 48, 33)]:
+    x = (torch.randn((P, T, 1, npix), device="cuda") + 1j * torch.randn((P, T, 1, npix), device="cuda")).to(torch.complex64) + 2.0
+    out = engine.tacaw_intensity(x)
+    assert torch.isfinite(out).all()
 torch.cuda.synchronize()
 print("sanitize case ok, level", level)
 PY
