@@ -168,6 +168,10 @@ constexpr bool row_mode_steps(int mode) { return mode == R_STEP || mode == R_STE
 
 // phases of the slice (R_STEP_PHASE) loaded straight into registers with streaming loads at the start of a unit (1) instead
 // of TMA -> landing buffer -> LDS (0): 8 B per pixel less through the L1 / shared-memory pipe, 16 more live registers
+// exp(i*phase) of the phase-format slice step evaluated for two pixels at a time (1) or one (0)
+#ifndef PSB_ROW_PAIR_CIS
+#define PSB_ROW_PAIR_CIS 1
+#endif
 #ifndef PSB_ROW_PHASE_LDG
 #define PSB_ROW_PHASE_LDG 0
 #endif
@@ -303,6 +307,18 @@ __global__ void __launch_bounds__(RowCfg<N, MODE>::kThreads, 1) fast_rows_kernel
                 [&](int e) { return lp[e * C::T]; },
                 [&](int e, cpx a) {
                     if constexpr (MODE == R_STEP_PHASE && PSB_ROW_PHASE_LDG) v[e] = fast::cmulp(a, cis1(tph[e]));
+                    else if constexpr (MODE == R_STEP_PHASE && PSB_ROW_PAIR_CIS) {
+                        // the last butterfly layer hands out positions k, k + 4, k + 8, k + 12: take them two at a time so the
+                        // range reduction of exp(i*phase) runs on the packed pipe (4 instead of 8 fp32 instructions per pair)
+                        if (((e >> 2) & 1) == 0) {
+                            v[e] = a;
+                        } else {
+                            cpx ea, eb;
+                            pair_cis(fast::c_make(ltf[(e - 4) * C::T], ltf[e * C::T]), ea, eb);
+                            v[e - 4] = fast::cmulp(v[e - 4], ea);
+                            v[e] = fast::cmulp(a, eb);
+                        }
+                    }
                     else if constexpr (MODE == R_STEP_PHASE) v[e] = fast::cmulp(a, cis1(ltf[e * C::T]));
                     else v[e] = fast::cmulp(a, lt[e * C::T]);
                 },
