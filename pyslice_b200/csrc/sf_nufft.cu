@@ -234,6 +234,18 @@ struct NufftXchg {
     __device__ __forceinline__ void mid_sync(int) const { __syncthreads(); }
 };
 
+// two adjacent packed complex values with one 128-bit load (p 16-byte aligned)
+__device__ __forceinline__ void load_pair(const cpx* p, cpx& a, cpx& b) {
+#if defined(__CUDA_ARCH__)
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p);
+    a = v.x;
+    b = v.y;
+#else
+    a = p[0];
+    b = p[1];
+#endif
+}
+
 template <int M>
 __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(const NufftParams p, const int n_tiles) {
     using C = NufftCfg<M>;
@@ -341,9 +353,10 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
             for (int pass = 0; pass < RW / 32; ++pass) {
                 const int r_first = RW * warp + 32 * pass;
                 const int r = r_first + lane;
-                float2 acc[C::W];
+                cpx acc[C::W];                                   // packed: one FFMA2 per record and column (weight broadcast to both halves)
 #pragma unroll
-                for (int cc = 0; cc < C::W; ++cc) acc[cc] = make_float2(0.f, 0.f);
+                for (int cc = 0; cc < C::W; ++cc) acc[cc] = fast::c_make(0.f, 0.f);
+                const cpx* s_e2 = reinterpret_cast<const cpx*>(s_e);
                 // records with cell in [r_first - 4, r_first + 35]: bins (r_first >> 3) - 1 .. (r_first >> 3) + 4
                 // staged records: branch-free body, four records per trip (their loads are independent, so the shared-memory
                 // latency is paid once per four; a record whose taps miss this lane's row contributes weight 0)
@@ -356,23 +369,30 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                         w[q] = (unsigned int)k < (unsigned int)kTaps ? ww : 0.f;
                     }
 #pragma unroll
-                    for (int q = 0; q < 4; ++q)
+                    for (int q = 0; q < 4; ++q) {
+                        const cpx w2 = fast::c_make(w[q], w[q]);
+                        // the record's W phase factors are contiguous: 128-bit broadcast loads, two columns each (ncu r2ak: the
+                        // kernel's busiest unit is the L1 / shared-memory pipe at 73 %, and this loop issues most of its loads)
 #pragma unroll
-                        for (int cc = 0; cc < C::W; ++cc) {
-                            const float2 e = s_e[(i + q) * C::W + cc];
-                            acc[cc].x = fmaf(w[q], e.x, acc[cc].x);
-                            acc[cc].y = fmaf(w[q], e.y, acc[cc].y);
+                        for (int cc = 0; cc < C::W; cc += 2) {
+                            cpx e0, e1;
+                            load_pair(s_e2 + (i + q) * C::W + cc, e0, e1);
+                            acc[cc] = fast::fma2(w2, e0, acc[cc]);
+                            acc[cc + 1] = fast::fma2(w2, e1, acc[cc + 1]);
                         }
+                    }
                 };
                 auto staged1 = [&](int i) {
                     const int k = ((r - (int)(s_rx[i] >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;
                     const float ww = s_w[i * kTaps + (k & (kTaps - 1))];
                     const float w = (unsigned int)k < (unsigned int)kTaps ? ww : 0.f;
+                    const cpx w2 = fast::c_make(w, w);
 #pragma unroll
-                    for (int cc = 0; cc < C::W; ++cc) {
-                        const float2 e = s_e[i * C::W + cc];
-                        acc[cc].x = fmaf(w, e.x, acc[cc].x);
-                        acc[cc].y = fmaf(w, e.y, acc[cc].y);
+                    for (int cc = 0; cc < C::W; cc += 2) {
+                        cpx e0, e1;
+                        load_pair(s_e2 + i * C::W + cc, e0, e1);
+                        acc[cc] = fast::fma2(w2, e0, acc[cc]);
+                        acc[cc + 1] = fast::fma2(w2, e1, acc[cc + 1]);
                     }
                 };
                 auto unstaged = [&](int i) {                     // beyond the staging area: from L2, phase factors on the fly
@@ -388,8 +408,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                             float2 e = ((p.ny % 2 == 0) && myc == p.ny / 2) ? make_float2(unit_phase_fast(p.ny / 2, v).x, 0.f)
                                                                              : unit_phase_fast(msc, v);
                             if (par) e = make_float2(-e.y, e.x);
-                            acc[cc].x = fmaf(w, e.x, acc[cc].x);
-                            acc[cc].y = fmaf(w, e.y, acc[cc].y);
+                            acc[cc] = fast::fma2(fast::c_make(w, w), fast::c_make(e.x, e.y), acc[cc]);
                         }
                     }
                 };
@@ -404,7 +423,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                 if (b_lo < 0) walk(s_xoff[kBins - 1], s_xoff[kBins]);                 // wraps around the periodic axis
                 walk(s_xoff[b_lo < 0 ? 0 : b_lo], s_xoff[(b_hi > kBins - 1 ? kBins - 1 : b_hi) + 1]);
                 if (b_hi > kBins - 1) walk(s_xoff[0], s_xoff[1]);
-                float2* cells = tile + (r + (r >> 4)) * C::W;
+                cpx* cells = reinterpret_cast<cpx*>(tile) + (r + (r >> 4)) * C::W;
 #pragma unroll
                 for (int cc = 0; cc < C::W; ++cc) cells[cc] = acc[cc];
             }

@@ -208,9 +208,10 @@ def test_hbn_multi_type_probes_vs_oracle():
             assert rel_l2(wf[p, f], ref[p, f]) < 1e-4
 
 
-@pytest.mark.parametrize("T", [20, 100, 500, 2000, 4000, 64, 97, 14, 331, 45, 6, 2])
+@pytest.mark.parametrize("T", [20, 100, 500, 2000, 4000, 64, 97, 14, 331, 45, 6, 2, 40, 60, 200, 250, 300, 1000])
 def test_tacaw_time_fft_lengths(T):
-    # 2^a 3^b 5^c lengths run the tiled mixed-radix kernel (tacaw_fast.cu), 97 / 14 / 331 the Bluestein line pass
+    # 2^a 3^b 5^c lengths run the tiled mixed-radix kernel (tacaw_fast.cu; 40 ... 1000: plans mixing the prime-factor radices
+    # 10 and 20 with 2, 3, 4, 5), 97 / 14 / 331 the Bluestein line pass
     from pyslice_b200 import engine
     rng = np.random.default_rng(T)
     P, nx, ny = 2, 8, 16

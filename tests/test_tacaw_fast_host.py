@@ -32,7 +32,7 @@ def reference(x):
     return np.abs(np.fft.fftshift(np.fft.fft(x - x.mean(axis=0, keepdims=True), axis=0), axes=0)) ** 2
 
 
-@pytest.mark.parametrize("T,npix,want_px", [(20, 130, 64), (100, 70, 64), (500, 19, 16), (2000, 9, 8), (4000, 5, 4),
+@pytest.mark.parametrize("T,npix,want_px", [(20, 130, 64), (100, 70, 64), (60, 40, 64), (200, 21, 32), (250, 17, 32), (1000, 9, 8), (500, 19, 16), (2000, 9, 8), (4000, 5, 4),
                                             (64, 33, 64), (45, 7, 64), (6, 3, 64), (2, 5, 64), (3, 4, 64), (5, 65, 64),
                                             (1500, 8, 8), (1600, 3, 8)])
 def test_tile_transform_matches_numpy(harness, T, npix, want_px):
