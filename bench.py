@@ -582,7 +582,10 @@ def main():
             pass
         traffic = traffic_doc.get("by_grid", {}).get(f"{nx}x{ny}", {}).get("dram_bytes_per_launch_pair",
                                                                           traffic_doc.get("slice_step_dram_bytes_per_launch") if nx == 256 else None)
-        fb = engine.batch_sizes(calc._plan, P, max(F, 1))[0]
+        fb, pb = engine.batch_sizes(calc._plan, P, max(F, 1))
+        by_grid = traffic_doc.get("by_grid", {}).get(f"{nx}x{ny}")
+        if traffic is not None and by_grid and by_grid.get("images_per_launch"):
+            traffic = traffic * (fb * pb) / by_grid["images_per_launch"]          # captured per launch pair of N images; scale to this run's batch
         cfg = config_block(wl, name, world, counts, A, P)
         cyc = FP32_SM_CYCLES_PER_PIXEL.get((max(nx, ny), "phase" if P == 1 else "c64")) if nx == ny else None
         sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
