@@ -4,7 +4,10 @@ usage: python tools/microbench_tacaw.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pyslice_b200 import engine
+from pyslice_b200 import engine, _lib
+if os.environ.get("PSB_VARIANT_LIB"):          # tuning experiments: time an alternative build of libpsb
+    _lib._lib = _lib.load(os.path.abspath(os.environ["PSB_VARIANT_LIB"]))
+    print("variant library:", os.environ["PSB_VARIANT_LIB"])
 CASES = [("C2: P=1, T=500, 256x256", 1, 500, 256, 256), ("C3 quarter: P=64, T=100, 512x512", 64, 100, 512, 512),
          ("C4 per GPU of 8: P=1, T=2000, 128x1024", 1, 2000, 128, 1024), ("C1: P=1, T=20, 256x256", 1, 20, 256, 256)]
 for name, P, T, nx, ny in CASES:
