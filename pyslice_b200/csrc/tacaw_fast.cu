@@ -188,16 +188,7 @@ int launch_tacaw_fast(const float2* wf, long long stride_probe, long long stride
         }
         case 32: return go<32, 256>(p, n_probes, s);
         case 16: return go<16, 256>(p, n_probes, s);
-        case 8: {
-            // EXPERIMENT (PSB_TACAW_LONG=1): whole-SM series as 4-pixel tiles, two 256-thread CTAs per SM, so that one tile's
-            // loads overlap the other's stages (32-byte segments: relies on L2 pairing the sectors of neighbouring tiles)
-            static const int long_mode = [] {
-                const char* e = std::getenv("PSB_TACAW_LONG");
-                return e ? std::atoi(e) : 0;
-            }();
-            if (one_per_sm && long_mode == 1 && (size_t)n_frames * 4 * sizeof(float2) <= (100u << 10)) return go<4, 256>(p, n_probes, s);
-            return one_per_sm ? go<8, 1024>(p, n_probes, s) : go<8, 256>(p, n_probes, s);
-        }
+        case 8: return one_per_sm ? go<8, 1024>(p, n_probes, s) : go<8, 256>(p, n_probes, s);
         case 4: return go<4, 1024>(p, n_probes, s);
         default: return fail(PSB_ERR_UNSUPPORTED, "tacaw fast path: frame count too large for a shared-memory tile");
     }
