@@ -92,3 +92,12 @@ def test_batch_and_chunk_sizing_rules(monkeypatch):
     assert engine.chunk_images(NS(nx=1024, ny=1024, nz=123), 100) == 9          # 1152 tiles = 3.9 rounds, not 8 -> 3.5 of 4
     assert engine.chunk_images(NS(nx=256, ny=256, nz=9), 2) == 10                # never more than the work there is
     assert engine.chunk_images(NS(nx=4096, ny=4096, nz=40), 1) == 1
+    # psi batches: L2-sized at 256 / 512 points, streaming-sized (up to 320 MB = 40 images, whole rounds of the one-CTA-per-SM
+    # column pass preferred) at 1024 points
+    cpu = NS(type="cpu")
+    fb, pb = engine.batch_sizes(NS(nx=256, ny=256, nz=512, device=cpu), 1, 500)
+    assert pb == 1 and 100 <= fb <= 160 and fb * 256 * 256 * 8 <= engine.PSI_BATCH_BYTES
+    fb, pb = engine.batch_sizes(NS(nx=512, ny=512, nz=67, device=cpu), 256, 100)
+    assert fb == 1 and pb * 512 * 512 * 8 <= engine.PSI_BATCH_BYTES and pb >= 32
+    fb, pb = engine.batch_sizes(NS(nx=1024, ny=1024, nz=123, device=cpu), 1, 250)
+    assert pb == 1 and 24 <= fb <= 40 and fb * 1024 * 1024 * 8 <= engine.PSI_BATCH_BYTES_STREAMING
