@@ -48,6 +48,12 @@ namespace {
 using fast::cpx;
 
 constexpr int kTaps = 8;
+// x bins the records are ordered by: kBinCells fine cells each.  The gather's warp of 32 rows needs the records of cells
+// [r - 4, r + 35]: six bins of 8 cells = 48 cells, or ten bins of 4 = exactly those 40 (17 % fewer records walked)
+#ifndef PSB_NUFFT_BIN_SHIFT
+#define PSB_NUFFT_BIN_SHIFT 2
+#endif
+constexpr int kBinShift = PSB_NUFFT_BIN_SHIFT, kBinCells = 1 << kBinShift;
 constexpr float kBeta = 2.30f * kTaps;
 constexpr int kMaxKeys = 8192;          // ntypes * bins the ordering kernel can histogram in shared memory
 
@@ -60,7 +66,7 @@ struct NufftParams {
     int cap, nz, ntypes, nx, ny;
     int npairs;                 // slice pairs per frame
     int frame0, pair_begin, pair_count;     // K2: this chunk covers frames [frame0, frame0 + nf) x pairs [pair_begin, pair_begin + pair_count)
-    int nb, log_m;              // x bins per pair (= M / 8), log2(M)
+    int nb, log_m;              // x bins per pair (= M / kBinCells), log2(M)
     // written by K1, read by K2
     int* xoff;                  // (F, npairs, ntypes*nb + 1) offsets into the pair's record range, by (type, bin)
     unsigned int* rx;           // (F, cap) records of a pair, ordered by (type, bin), list order inside
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(256) nufft_prep_kernel(const NufftParams p) {
     const int begin = off[s0 * p.ntypes], end = off[s1 * p.ntypes], n = end - begin;
     const unsigned int* ux = p.ux + (long long)f * p.cap;
     const unsigned int* uy = p.uy + (long long)f * p.cap;
-    const int shift = 32 - p.log_m + 3;                                // bin = fine cell / 8
+    const int shift = 32 - p.log_m + kBinShift;                        // bin = fine cell / kBinCells
 
     auto seg_of = [&](int i) {                                         // list index -> segment (2 * ntypes candidates)
         int seg = s0 * p.ntypes;
@@ -218,7 +224,7 @@ struct NufftCfg {
     static constexpr int kRows = M + M / 16;         // padded
     static constexpr size_t kTileBytes = (size_t)kRows * W * sizeof(float2);
     static constexpr int kStage = W == 4 ? 1536 : 1024;      // records of one atom type staged in shared memory (more: read from L2)
-    static constexpr size_t kEOffset = (kTileBytes + 3 * kStage * sizeof(unsigned int) + (M / 8 + 1) * sizeof(int) + (M / 2) * sizeof(float) + 15) / 16 * 16;
+    static constexpr size_t kEOffset = (kTileBytes + 3 * kStage * sizeof(unsigned int) + (M / kBinCells + 1) * sizeof(int) + (M / 2) * sizeof(float) + 15) / 16 * 16;
     static constexpr size_t kSmem = kEOffset + (size_t)kStage * W * sizeof(float2) + (size_t)kStage * 8 * sizeof(float);
     static constexpr int kLogM = M == 2048 ? 11 : 10;
 };
@@ -254,8 +260,8 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     unsigned int* s_rx = reinterpret_cast<unsigned int*>(smem_raw + C::kTileBytes);      // [kStage] records of the current (pair, type)
     unsigned int* s_ry = s_rx + C::kStage;
     unsigned int* s_rp = s_ry + C::kStage;
-    int* s_xoff = reinterpret_cast<int*>(s_rp + C::kStage);                              // [M / 8 + 1]
-    float* s_dec = reinterpret_cast<float*>(s_xoff + M / 8 + 1);                         // [nx]
+    int* s_xoff = reinterpret_cast<int*>(s_rp + C::kStage);                              // [M / kBinCells + 1]
+    float* s_dec = reinterpret_cast<float*>(s_xoff + M / kBinCells + 1);                 // [nx]
     float2* s_e = reinterpret_cast<float2*>(smem_raw + C::kEOffset);                     // [kStage][W] exp(-2 pi i ky y) per record and column
     float* s_w = reinterpret_cast<float*>(s_e + (size_t)C::kStage * C::W);               // [kStage][8] tap weights
     const int tid = threadIdx.x, c = tid % C::W, j = tid / C::W;
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     tw.load(p.tw, j);
     for (int i = tid; i < nx; i += C::kThreads) s_dec[i] = p.dec[i];
     const NufftXchg<M> xc{reinterpret_cast<cpx*>(tile), c};
-    const int nkeys = p.ntypes * (M / 8);
+    const int nkeys = p.ntypes * (M / kBinCells);
     const int nseg = p.nz * p.ntypes;
     const int tiles_per_pair = p.ny / C::W;
     constexpr unsigned int kFracBits = 32 - C::kLogM;
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
     const int warp = tid >> 5, lane = tid & 31;
     constexpr int RW = M / 16;                                    // rows per warp
     constexpr int kLogRW = C::kLogM - 4;
-    constexpr int kBins = M / 8;                                  // x bins of 8 fine cells (the records are ordered by them)
+    constexpr int kBins = M / kBinCells;                          // x bins (the records are ordered by them)
     const int tile0 = (int)((long long)n_tiles * blockIdx.x / gridDim.x);
     const int tile1 = (int)((long long)n_tiles * (blockIdx.x + 1) / gridDim.x);
     int staged_img = -1, cur_img = -1, type_r0 = 0, type_r1 = 0;
@@ -300,7 +306,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
             rwt = p.rwt + rbase * kTaps;
             corner = p.corner + ((long long)f * p.npairs + m) * p.ntypes * 2;
             type_r0 = xoff[0];                                   // record range of type 0 (the only one in single-type runs)
-            type_r1 = xoff[M / 8];
+            type_r1 = xoff[kBins];
         }
         cpx acc_out[8];
 #pragma unroll
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
             }
             // ---- stage this (pair, type)'s records and bin offsets (kept across the pair's column tiles when there is
             //      one atom type), clear the tile
-            const int r0 = z == 0 ? type_r0 : xoff[z * (M / 8)], r1 = z == 0 ? type_r1 : xoff[(z + 1) * (M / 8)];
+            const int r0 = z == 0 ? type_r0 : xoff[z * kBins], r1 = z == 0 ? type_r1 : xoff[(z + 1) * kBins];
             if (p.ntypes > 1 || staged_img != img) {
                 const int nstage = (r1 - r0) < C::kStage ? (r1 - r0) : C::kStage;
                 for (int i = tid; i < nstage; i += C::kThreads) {
@@ -326,7 +332,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                 }
                 for (int i = tid; i < nstage * 2; i += C::kThreads)
                     reinterpret_cast<float4*>(s_w)[i] = reinterpret_cast<const float4*>(rwt + (long long)r0 * kTaps)[i];
-                for (int i = tid; i <= M / 8; i += C::kThreads) s_xoff[i] = xoff[z * (M / 8) + i] - r0;
+                for (int i = tid; i <= kBins; i += C::kThreads) s_xoff[i] = xoff[z * kBins + i] - r0;
                 staged_img = img;
             }
             {   // phase factors of the staged records for this tile's columns (a record is used by up to two warps and eight taps)
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
 #pragma unroll
                 for (int cc = 0; cc < C::W; ++cc) acc[cc] = fast::c_make(0.f, 0.f);
                 const cpx* s_e2 = reinterpret_cast<const cpx*>(s_e);
-                // records with cell in [r_first - 4, r_first + 35]: bins (r_first >> 3) - 1 .. (r_first >> 3) + 4
+                // records with cell in [r_first - 4, r_first + 35]: bins b_lo .. b_hi below
                 // staged records: branch-free body, four records per trip (their loads are independent, so the shared-memory
                 // latency is paid once per four; a record whose taps miss this lane's row contributes weight 0)
                 auto staged4 = [&](int i) {
@@ -419,7 +425,7 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                     for (; i < i1s; ++i) staged1(i);
                     for (; i < i1; ++i) unstaged(i);
                 };
-                const int b_lo = (r_first >> 3) - 1, b_hi = (r_first >> 3) + 4;
+                const int b_lo = (r_first - 4) >> kBinShift, b_hi = (r_first + 35) >> kBinShift;      // -4 >> s = -1
                 if (b_lo < 0) walk(s_xoff[kBins - 1], s_xoff[kBins]);                 // wraps around the periodic axis
                 walk(s_xoff[b_lo < 0 ? 0 : b_lo], s_xoff[(b_hi > kBins - 1 ? kBins - 1 : b_hi) + 1]);
                 if (b_hi > kBins - 1) walk(s_xoff[0], s_xoff[1]);
@@ -531,7 +537,7 @@ int sf_mode() { return g_sf_mode.load(); }
 bool sf_nufft_supported(int ntypes, int nx, int ny) {
     if (nx != 512 && nx != 1024) return false;
     const int W = nx == 1024 ? 4 : 8;
-    return ny % W == 0 && ntypes * (nx / 4) <= kMaxKeys;
+    return ny % W == 0 && ntypes * (2 * nx / kBinCells) <= kMaxKeys;
 }
 
 // dense enough for the transform to beat the direct sum: atoms per slice pair and type (measured crossover)
@@ -569,7 +575,7 @@ int nufft_params(const int* offsets, const unsigned int* ux, const unsigned int*
     NufftParams p;
     std::memset(&p, 0, sizeof(p));
     p.offsets = offsets; p.ux = ux; p.uy = uy; p.cap = cap; p.nz = nz; p.ntypes = ntypes; p.nx = nx; p.ny = ny;
-    p.npairs = (nz + 1) / 2; p.nb = M / 8; p.log_m = M == 2048 ? 11 : 10;
+    p.npairs = (nz + 1) / 2; p.nb = M / kBinCells; p.log_m = M == 2048 ? 11 : 10;
     p.ff = ff;
     int rc = dec_table(nx, &p.dec, owner);
     if (rc != PSB_OK) return rc;
