@@ -50,6 +50,11 @@ using fast::cpx;
 constexpr int kTaps = 8;
 // x bins the records are ordered by: kBinCells fine cells each.  The gather's warp of 32 rows needs the records of cells
 // [r - 4, r + 35]: six bins of 8 cells = 48 cells, or ten bins of 4 = exactly those 40 (17 % fewer records walked)
+// rows per lane of the gather: 2 shares a record's fetches between two rows 32 apart and narrows the warp's window, but
+// measured slower (11.65 against 10.65 ms per 8 frames of C4: registers, profiles/r2ar_nufft_rows_per_lane.txt)
+#ifndef PSB_NUFFT_ROWS_PER_LANE
+#define PSB_NUFFT_ROWS_PER_LANE 1
+#endif
 #ifndef PSB_NUFFT_BIN_SHIFT
 #define PSB_NUFFT_BIN_SHIFT 2
 #endif
@@ -355,56 +360,67 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
             //      to its W column accumulators and stores the finished cells once.  No read-modify-write of shared
             //      memory, no ordering between records beyond program order, no barrier: the earlier scatter forms were
             //      bound by exactly those (profiles/r2_nufft_spread_history.txt).
+            // A lane takes RPL rows 32 apart (1 by default; with 2 the record's cell, tap index -- k and k + 32 pick the same
+            // weight slot -- and phase factors are fetched once for both rows, and the warp's window is 64 + 8 cells instead of
+            // 2 x (32 + 8))
+            constexpr int RPL = (C::W == 4 && PSB_NUFFT_ROWS_PER_LANE == 2) ? 2 : 1;
 #pragma unroll 1
-            for (int pass = 0; pass < RW / 32; ++pass) {
-                const int r_first = RW * warp + 32 * pass;
+            for (int pass = 0; pass < RW / (32 * RPL); ++pass) {
+                const int r_first = RW * warp + 32 * RPL * pass;
                 const int r = r_first + lane;
-                cpx acc[C::W];                                   // packed: one FFMA2 per record and column (weight broadcast to both halves)
+                cpx acc[RPL][C::W];                              // packed: one FFMA2 per record, row and column (weight broadcast to both halves)
 #pragma unroll
-                for (int cc = 0; cc < C::W; ++cc) acc[cc] = fast::c_make(0.f, 0.f);
+                for (int rr = 0; rr < RPL; ++rr)
+#pragma unroll
+                    for (int cc = 0; cc < C::W; ++cc) acc[rr][cc] = fast::c_make(0.f, 0.f);
                 const cpx* s_e2 = reinterpret_cast<const cpx*>(s_e);
-                // records with cell in [r_first - 4, r_first + 35]: bins b_lo .. b_hi below
-                // staged records: branch-free body, four records per trip (their loads are independent, so the shared-memory
-                // latency is paid once per four; a record whose taps miss this lane's row contributes weight 0)
-                auto staged4 = [&](int i) {
-                    float w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int k = ((r - (int)(s_rx[i + q] >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;      // periodic distance, in taps
-                        const float ww = s_w[(i + q) * kTaps + (k & (kTaps - 1))];
-                        w[q] = (unsigned int)k < (unsigned int)kTaps ? ww : 0.f;
-                    }
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const cpx w2 = fast::c_make(w[q], w[q]);
-                        // the record's W phase factors are contiguous: 128-bit broadcast loads, two columns each (ncu r2ak: the
-                        // kernel's busiest unit is the L1 / shared-memory pipe at 73 %, and this loop issues most of its loads)
-#pragma unroll
-                        for (int cc = 0; cc < C::W; cc += 2) {
-                            cpx e0, e1;
-                            load_pair(s_e2 + (i + q) * C::W + cc, e0, e1);
-                            acc[cc] = fast::fma2(w2, e0, acc[cc]);
-                            acc[cc + 1] = fast::fma2(w2, e1, acc[cc + 1]);
-                        }
+                // weights of one record for the lane's rows: the tap that lands on the row, or 0
+                auto taps = [&](unsigned int rxv, const float* wrec, float* w) {
+                    const int cell = (int)(rxv >> kFracBits);
+                    const int k0 = ((r - cell + 3 + M / 2) & (M - 1)) - M / 2;           // periodic distance, in taps
+                    const float ww = wrec[k0 & (kTaps - 1)];
+                    w[0] = (unsigned int)k0 < (unsigned int)kTaps ? ww : 0.f;
+                    if (RPL == 2) {
+                        const int k1 = ((r + 32 - cell + 3 + M / 2) & (M - 1)) - M / 2;  // same slot: 32 is a multiple of kTaps
+                        w[RPL - 1] = (unsigned int)k1 < (unsigned int)kTaps ? ww : 0.f;
                     }
                 };
-                auto staged1 = [&](int i) {
-                    const int k = ((r - (int)(s_rx[i] >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;
-                    const float ww = s_w[i * kTaps + (k & (kTaps - 1))];
-                    const float w = (unsigned int)k < (unsigned int)kTaps ? ww : 0.f;
-                    const cpx w2 = fast::c_make(w, w);
+                auto add_record = [&](int i, const float* w) {
+                    // the record's W phase factors are contiguous: 128-bit broadcast loads, two columns each (ncu r2ak: the
+                    // kernel's busiest unit is the L1 / shared-memory pipe at 73 %, and this loop issues most of its loads)
 #pragma unroll
                     for (int cc = 0; cc < C::W; cc += 2) {
                         cpx e0, e1;
                         load_pair(s_e2 + i * C::W + cc, e0, e1);
-                        acc[cc] = fast::fma2(w2, e0, acc[cc]);
-                        acc[cc + 1] = fast::fma2(w2, e1, acc[cc + 1]);
+#pragma unroll
+                        for (int rr = 0; rr < RPL; ++rr) {
+                            const cpx w2 = fast::c_make(w[rr], w[rr]);
+                            acc[rr][cc] = fast::fma2(w2, e0, acc[rr][cc]);
+                            acc[rr][cc + 1] = fast::fma2(w2, e1, acc[rr][cc + 1]);
+                        }
                     }
                 };
+                // staged records: branch-free body, four records per trip (their loads are independent, so the shared-memory
+                // latency is paid once per four; a record whose taps miss this lane's rows contributes weight 0)
+                auto staged4 = [&](int i) {
+                    float w[4][RPL];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) taps(s_rx[i + q], s_w + (i + q) * kTaps, w[q]);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) add_record(i + q, w[q]);
+                };
+                auto staged1 = [&](int i) {
+                    float w[RPL];
+                    taps(s_rx[i], s_w + i * kTaps, w);
+                    add_record(i, w);
+                };
                 auto unstaged = [&](int i) {                     // beyond the staging area: from L2, phase factors on the fly
-                    const int k = ((r - (int)(rx[r0 + i] >> kFracBits) + 3 + M / 2) & (M - 1)) - M / 2;
-                    if ((unsigned int)k < (unsigned int)kTaps) {
-                        const float w = rwt[(long long)(r0 + i) * kTaps + k];
+                    float w[RPL];
+                    taps(rx[r0 + i], rwt + (long long)(r0 + i) * kTaps, w);
+                    bool any = false;
+#pragma unroll
+                    for (int rr = 0; rr < RPL; ++rr) any = any || w[rr] != 0.f;
+                    if (any) {
                         const unsigned int v = ry[r0 + i];
                         const bool par = rpar[r0 + i] != 0;
 #pragma unroll
@@ -414,7 +430,9 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                             float2 e = ((p.ny % 2 == 0) && myc == p.ny / 2) ? make_float2(unit_phase_fast(p.ny / 2, v).x, 0.f)
                                                                              : unit_phase_fast(msc, v);
                             if (par) e = make_float2(-e.y, e.x);
-                            acc[cc] = fast::fma2(fast::c_make(w, w), fast::c_make(e.x, e.y), acc[cc]);
+#pragma unroll
+                            for (int rr = 0; rr < RPL; ++rr)
+                                acc[rr][cc] = fast::fma2(fast::c_make(w[rr], w[rr]), fast::c_make(e.x, e.y), acc[rr][cc]);
                         }
                     }
                 };
@@ -425,13 +443,18 @@ __global__ void __launch_bounds__(NufftCfg<M>::kThreads, 1) nufft_cols_kernel(co
                     for (; i < i1s; ++i) staged1(i);
                     for (; i < i1; ++i) unstaged(i);
                 };
-                const int b_lo = (r_first - 4) >> kBinShift, b_hi = (r_first + 35) >> kBinShift;      // -4 >> s = -1
+                // records with cell in [r_first - 4, r_first + 32 RPL + 3]
+                const int b_lo = (r_first - 4) >> kBinShift, b_hi = (r_first + 32 * RPL + 3) >> kBinShift;      // -4 >> s = -1
                 if (b_lo < 0) walk(s_xoff[kBins - 1], s_xoff[kBins]);                 // wraps around the periodic axis
                 walk(s_xoff[b_lo < 0 ? 0 : b_lo], s_xoff[(b_hi > kBins - 1 ? kBins - 1 : b_hi) + 1]);
                 if (b_hi > kBins - 1) walk(s_xoff[0], s_xoff[1]);
-                cpx* cells = reinterpret_cast<cpx*>(tile) + (r + (r >> 4)) * C::W;
 #pragma unroll
-                for (int cc = 0; cc < C::W; ++cc) cells[cc] = acc[cc];
+                for (int rr = 0; rr < RPL; ++rr) {
+                    const int rw = r + 32 * rr;
+                    cpx* cells = reinterpret_cast<cpx*>(tile) + (rw + (rw >> 4)) * C::W;
+#pragma unroll
+                    for (int cc = 0; cc < C::W; ++cc) cells[cc] = acc[rr][cc];
+                }
             }
             __syncthreads();
             // ---- M-point transform along x, in place in the tile
